@@ -1,0 +1,198 @@
+/*
+ * include/lbm_b200.h -- C ABI of the B200-native lattice-Boltzmann sweep.
+ *
+ * This is the drop-in boundary for the hot path of hackerbruecke/lbm: the
+ * three calls  domain->stream(); domain->swap(); domain->collide();  of
+ * src/main.cpp:50-52, together with the state they act on (the two lattices
+ * of include/domain.h:13-14) and the read-out of io/vtk.hpp:62-73.
+ * The reference has no FFI of its own -- its operator API is the C++ template
+ * surface (Collision/Domain/Cell) -- so these entry points are what the
+ * C++ wrappers under include/lbm/ (same class names as the reference) bind to.
+ * Plain pointers and sizes only; no CUDA, torch or C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative LBM_B200_E* code on
+ *     failure; lbm_b200_last_error() then holds a message (thread-local).
+ *     Nothing throws across this boundary.  (Reference: exceptions caught in
+ *     main, src/main.cpp:68-71; the C++ wrapper re-throws.)
+ *   - host arrays over cells use the reference's Domain::idx order
+ *     (domain.hpp:61-64):  idx = x + (xl+2)*y + (xl+2)*(yl+2)*z, ghost shell
+ *     included, local to the handle (a slab has zl_local+2 planes).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with LBM_B200_ECUDA.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_B200_ABI_VERSION 1
+
+/* error codes */
+enum {
+    LBM_B200_OK = 0,
+    LBM_B200_EINVAL = -1,   /* bad argument                                   */
+    LBM_B200_ECUDA = -2,    /* CUDA runtime error / no device                  */
+    LBM_B200_ENOMEM = -3,   /* allocation failed                               */
+    LBM_B200_ESTATE = -4,   /* call not valid in the current state             */
+    LBM_B200_ETIMEOUT = -5  /* neighbour slab did not signal in time           */
+};
+
+/* Cell handler kinds == the reference's collision classes. */
+enum {
+    LBM_B200_FLUID = 0,      /* BGKCollision            collision.h:64-71      */
+    LBM_B200_NOSLIP = 1,     /* NoSlipBoundary          boundary.hpp:15-31     */
+    LBM_B200_MOVINGWALL = 2, /* MovingWallBoundary      boundary.hpp:44-68     */
+    LBM_B200_FREESLIP = 3,   /* FreeSlipBoundary        boundary.hpp:80-115    */
+    LBM_B200_OUTFLOW = 4,    /* OutflowBoundary         boundary.hpp:129-150   */
+    LBM_B200_INFLOW = 5,     /* InflowBoundary          boundary.hpp:165-181   */
+    LBM_B200_PRESSURE = 6,   /* PressureBoundary        boundary.hpp:195-214   */
+    LBM_B200_NULL = 7,       /* NullCollision           collision.h:74-86      */
+    LBM_B200_PARALLEL = 8,   /* parallel::ParallelBoundary (no-op) parallel.h:11-23 */
+    LBM_B200_PERIODIC = 9    /* extension (not in the reference): a ghost cell  */
+                             /* that mirrors its periodically wrapped interior  */
+                             /* image; equals the ghost-copy recipe of SURVEY 8c */
+};
+
+/* One boundary handler object (what BoundaryKeeper::get_collision creates,
+ * boundary.h:86-91): kind + constructor arguments. */
+typedef struct {
+    int32_t kind;
+    int32_t _pad;
+    double v[3];   /* wall_velocity (boundary.h:23) / inflow_velocity (boundary.h:54) */
+    double rho;    /* reference_density (boundary.h:44,53) / input_density (boundary.h:65) */
+} lbm_b200_bc;
+
+/* arithmetic modes */
+enum {
+    LBM_B200_FAST = 0,  /* reciprocals + FMA contraction; differs from the       */
+                        /* reference by rounding only (gate: 1e-12 relative)     */
+    LBM_B200_EXACT = 1  /* the reference's expression association with true      */
+                        /* divisions and no FMA: bit-identical to the CPU build  */
+};
+
+/* population layouts for upload/download */
+enum {
+    LBM_B200_AOS = 0,   /* f[idx*Q + q]  -- the reference's Cell array          */
+    LBM_B200_SOA = 1    /* f[q*ncell + idx]                                     */
+};
+/* which of the reference's two lattices (domain.h:13-14) */
+enum {
+    LBM_B200_COLLIDE_FIELD = 0,  /* what Domain::cell() addresses              */
+    LBM_B200_STREAM_FIELD = 1
+};
+
+typedef struct lbm_b200 lbm_b200_t;
+
+const char* lbm_b200_last_error(void);
+int lbm_b200_abi_version(void);
+/* number of visible CUDA devices (0 without a GPU; never fails) */
+int lbm_b200_device_count(void);
+
+/* --- lattice descriptors (model.h:13-134), host side, no GPU needed -------- */
+/* velocities: Q*3 doubles (the reference stores them as double), weights: Q  */
+int lbm_b200_model(int Q, double* velocities, double* weights);
+int lbm_b200_model_inv(int Q, int q);
+int lbm_b200_model_velocity_index(int Q, int u, int v, int w);
+
+/* --- life cycle ------------------------------------------------------------ */
+/* Domain<M>(xl,yl,zl,collision) with BGKCollision<M>(tau)  (domain.hpp:87-98,
+ * collision.hpp:55-58).  Both lattices start at the weights (cell.hpp:9-15),
+ * every cell -- ghost shell included -- has the fluid handler.
+ * device < 0 selects the current CUDA device. */
+int lbm_b200_create(lbm_b200_t** h, int Q, uint64_t xl, uint64_t yl, uint64_t zl,
+                    double tau, int device);
+/* One z-slab of a global domain (replaces the intent of parallel.h:11-23 and
+ * Domain::create_subdomain, domain.hpp:197-248): this handle owns the global
+ * interior planes z_first .. z_first+zl_local-1 (1-based) of zl_global, plus one
+ * ghost plane on each side. */
+int lbm_b200_create_slab(lbm_b200_t** h, int Q, uint64_t xl, uint64_t yl, uint64_t zl_global,
+                         uint64_t z_first, uint64_t zl_local, double tau, int device);
+int lbm_b200_destroy(lbm_b200_t* h);
+
+int lbm_b200_set_arithmetic(lbm_b200_t* h, int mode);
+int lbm_b200_set_tau(lbm_b200_t* h, double tau);
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL
+ * returns to the handle's own stream */
+int lbm_b200_set_stream(lbm_b200_t* h, void* cuda_stream);
+
+/* --- geometry (Domain::setBoundaryCondition, domain.hpp:175-194, and
+ *     Domain::set_nonfluid_cells_nullcollide, domain.hpp:101-113) ------------ */
+/* kind: one LBM_B200_* per local cell; bc_id: index into table for cells whose
+ * kind takes parameters (may be NULL if n_table <= 1; then id 0 is used). */
+int lbm_b200_set_geometry(lbm_b200_t* h, const uint8_t* kind, const uint16_t* bc_id,
+                          const lbm_b200_bc* table, int n_table);
+/* the same through boxes applied in order, last writer wins (io/scenario.h:
+ * 91-128 -> domain.hpp:185-193); box i = 6 inclusive GLOBAL indices
+ * x0,xE,y0,yE,z0,zE and uses table[i].  Starts from the current geometry. */
+int lbm_b200_set_boxes(lbm_b200_t* h, const uint64_t* boxes6, const lbm_b200_bc* table, int n);
+/* interior fluid mask like the POINT_DATA of a legacy-VTK file (io/vtk.hpp:
+ * 137-150): xl*yl*zl_local bytes, 0 => NoSlipBoundary.  Applied to BOTH lattices
+ * (the reference tags the collide field only; see DESIGN.md "deviations"). */
+int lbm_b200_set_fluid_mask(lbm_b200_t* h, const uint8_t* mask);
+int lbm_b200_get_kind(lbm_b200_t* h, uint8_t* kind);
+
+/* --- state ------------------------------------------------------------------ */
+int lbm_b200_upload_populations(lbm_b200_t* h, const double* f, int layout, int field);
+int lbm_b200_download_populations(lbm_b200_t* h, double* f, int layout, int field);
+/* f = feq(rho,u) per local cell from host arrays rho[ncell], u[ncell*3] (idx
+ * order), evaluated on the device with compute_feq's association
+ * (collision.hpp:34-51 via Cell::equilibrium, cell.hpp:55-59) */
+int lbm_b200_init_equilibrium(lbm_b200_t* h, const double* rho, const double* u);
+
+/* --- the hot path: n x { stream(); swap(); collide(); }  (src/main.cpp:50-52) */
+int lbm_b200_step(lbm_b200_t* h, uint64_t n_steps);
+int lbm_b200_sync(lbm_b200_t* h);
+/* GPU time of the last lbm_b200_step call (CUDA events on the handle's stream) */
+int lbm_b200_elapsed_ms(lbm_b200_t* h, double* ms);
+/* kernels launched by this handle so far */
+int lbm_b200_launch_count(lbm_b200_t* h, uint64_t* n);
+uint64_t lbm_b200_steps_done(lbm_b200_t* h);
+
+/* --- read-out (io/vtk.hpp:62-73): interior cells, z,y,x order --------------- */
+/* rho: xl*yl*zl_local doubles, u: 3x that (may each be NULL) */
+int lbm_b200_macroscopic(lbm_b200_t* h, double* rho, double* u);
+/* reductions for physics checks: sum of density, sum of |u|^2, max |u| over
+ * interior FLUID cells of this slab */
+int lbm_b200_diagnostics(lbm_b200_t* h, double* mass, double* kinetic, double* umax);
+
+/* --- multi-GPU z-slabs -------------------------------------------------------
+ * After a step, slab r's top interior plane populations with c_z=+1 must appear
+ * in slab r+1's bottom ghost plane and vice versa.  Three transports:
+ *  (1) split-phase with an external transport (NCCL through torch.distributed):
+ *        step_edges -> [send/recv the halo planes] -> step_interior -> step_finish
+ *  (2) direct peer stores from the sweep kernel (CUDA P2P in one process, CUDA
+ *      IPC across processes): connect once, then lbm_b200_step as usual;
+ *  (3) in-process helper lbm_b200_group_* driving N slabs from one host thread.
+ */
+enum { LBM_B200_DOWN = 0, LBM_B200_UP = 1 };
+/* number of populations crossing an interface per direction (5/5/9) and the
+ * byte size of one x-y plane of one population (contiguous in device memory) */
+int lbm_b200_halo_layout(lbm_b200_t* h, int* n_q, size_t* plane_bytes);
+/* device pointer of the k-th plane to send to / receive from the neighbour on
+ * `side`, inside physical buffer 0 or 1.  Send planes are the slab's edge
+ * interior planes (c_z=+1 populations for UP, c_z=-1 for DOWN); receive planes
+ * are the ghost planes (c_z=-1 populations arrive from UP, c_z=+1 from DOWN). */
+int lbm_b200_halo_plane(lbm_b200_t* h, int buffer, int side, int k, int recv, void** device_ptr);
+/* physical buffer the step in flight writes (the one to exchange) */
+int lbm_b200_dst_buffer(lbm_b200_t* h);
+int lbm_b200_step_edges(lbm_b200_t* h);     /* sweep the two edge planes         */
+int lbm_b200_step_interior(lbm_b200_t* h);  /* sweep the remaining planes        */
+int lbm_b200_step_finish(lbm_b200_t* h);    /* swap (after the exchange landed)  */
+/* CUDA-IPC export of this slab's memory (64-byte handles) and connection to a
+ * neighbour's export; side = LBM_B200_UP / LBM_B200_DOWN */
+#define LBM_B200_EXPORT_BYTES 256
+int lbm_b200_export(lbm_b200_t* h, void* blob /*LBM_B200_EXPORT_BYTES*/);
+int lbm_b200_connect(lbm_b200_t* h, int side, const void* blob);
+/* same-process variant */
+int lbm_b200_connect_local(lbm_b200_t* h, int side, lbm_b200_t* neighbour);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

@@ -1,0 +1,282 @@
+"""ctypes binding of the C ABI in include/lbm_b200.h (lbm_b200/liblbm_b200.so).
+
+This is the Python-side stub the tests and bench.py use; the reference-facing
+host surface is the C++ one under include/lbm/.  There is no fallback: if the
+shared library is missing, import fails; if no CUDA device is present, every
+compute entry point raises LbmError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblbm_b200.so")
+
+FLUID, NOSLIP, MOVINGWALL, FREESLIP, OUTFLOW, INFLOW, PRESSURE, NULL, PARALLEL, PERIODIC = range(10)
+FAST, EXACT = 0, 1
+AOS, SOA = 0, 1
+COLLIDE_FIELD, STREAM_FIELD = 0, 1
+DOWN, UP = 0, 1
+EXPORT_BYTES = 256
+
+# every symbol include/lbm_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "lbm_b200_last_error", "lbm_b200_abi_version", "lbm_b200_device_count",
+    "lbm_b200_model", "lbm_b200_model_inv", "lbm_b200_model_velocity_index",
+    "lbm_b200_create", "lbm_b200_create_slab", "lbm_b200_destroy",
+    "lbm_b200_set_arithmetic", "lbm_b200_set_tau", "lbm_b200_set_stream",
+    "lbm_b200_set_geometry", "lbm_b200_set_boxes", "lbm_b200_set_fluid_mask", "lbm_b200_get_kind",
+    "lbm_b200_upload_populations", "lbm_b200_download_populations", "lbm_b200_init_equilibrium",
+    "lbm_b200_step", "lbm_b200_sync", "lbm_b200_elapsed_ms", "lbm_b200_launch_count", "lbm_b200_steps_done",
+    "lbm_b200_macroscopic", "lbm_b200_diagnostics",
+    "lbm_b200_halo_layout", "lbm_b200_halo_plane", "lbm_b200_dst_buffer",
+    "lbm_b200_step_edges", "lbm_b200_step_interior", "lbm_b200_step_finish",
+    "lbm_b200_export", "lbm_b200_connect", "lbm_b200_connect_local",
+]
+
+
+class LbmError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("lbm_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class Bc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("v", C.c_double * 3), ("rho", C.c_double)]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("%s not found: build it with `make` (python -c 'import __graft_entry__ as g; g.build()'); "
+                      "there is no CPU fallback" % LIB_PATH)
+lib = C.CDLL(LIB_PATH)
+
+_H = C.c_void_p
+lib.lbm_b200_last_error.restype = C.c_char_p
+lib.lbm_b200_steps_done.restype = C.c_uint64
+lib.lbm_b200_steps_done.argtypes = [_H]
+lib.lbm_b200_model.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+lib.lbm_b200_create.argtypes = [C.POINTER(_H), C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_int]
+lib.lbm_b200_create_slab.argtypes = [C.POINTER(_H), C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                     C.c_uint64, C.c_double, C.c_int]
+lib.lbm_b200_destroy.argtypes = [_H]
+lib.lbm_b200_set_arithmetic.argtypes = [_H, C.c_int]
+lib.lbm_b200_set_tau.argtypes = [_H, C.c_double]
+lib.lbm_b200_set_stream.argtypes = [_H, C.c_void_p]
+lib.lbm_b200_set_geometry.argtypes = [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+lib.lbm_b200_set_boxes.argtypes = [_H, C.c_void_p, C.c_void_p, C.c_int]
+lib.lbm_b200_set_fluid_mask.argtypes = [_H, C.c_void_p]
+lib.lbm_b200_get_kind.argtypes = [_H, C.c_void_p]
+lib.lbm_b200_upload_populations.argtypes = [_H, C.c_void_p, C.c_int, C.c_int]
+lib.lbm_b200_download_populations.argtypes = [_H, C.c_void_p, C.c_int, C.c_int]
+lib.lbm_b200_init_equilibrium.argtypes = [_H, C.c_void_p, C.c_void_p]
+lib.lbm_b200_step.argtypes = [_H, C.c_uint64]
+lib.lbm_b200_sync.argtypes = [_H]
+lib.lbm_b200_elapsed_ms.argtypes = [_H, C.POINTER(C.c_double)]
+lib.lbm_b200_launch_count.argtypes = [_H, C.POINTER(C.c_uint64)]
+lib.lbm_b200_macroscopic.argtypes = [_H, C.c_void_p, C.c_void_p]
+lib.lbm_b200_diagnostics.argtypes = [_H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+lib.lbm_b200_halo_layout.argtypes = [_H, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+lib.lbm_b200_halo_plane.argtypes = [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+lib.lbm_b200_dst_buffer.argtypes = [_H]
+lib.lbm_b200_step_edges.argtypes = [_H]
+lib.lbm_b200_step_interior.argtypes = [_H]
+lib.lbm_b200_step_finish.argtypes = [_H]
+lib.lbm_b200_export.argtypes = [_H, C.c_void_p]
+lib.lbm_b200_connect.argtypes = [_H, C.c_int, C.c_void_p]
+lib.lbm_b200_connect_local.argtypes = [_H, C.c_int, _H]
+
+
+def _check(rc):
+    if rc != 0:
+        raise LbmError(rc, lib.lbm_b200_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    return lib.lbm_b200_device_count()
+
+
+def model(Q):
+    """(velocities[Q,3], weights[Q]) of model.h's d3q15/d3q19/d3q27."""
+    c = np.zeros((Q, 3))
+    w = np.zeros(Q)
+    _check(lib.lbm_b200_model(Q, c.ctypes.data, w.ctypes.data))
+    return c, w
+
+
+def velocity_index(Q, u, v, w):
+    r = lib.lbm_b200_model_velocity_index(Q, u, v, w)
+    if r < -1:
+        _check(r)
+    return r
+
+
+def _boxes_arrays(boxes):
+    """boxes: list of (kind, v3, rho, (x0,xE,y0,yE,z0,zE)) as tests/_oracle.py builds them."""
+    n = len(boxes)
+    ext = np.zeros((max(n, 1), 6), dtype=np.uint64)
+    tab = (Bc * max(n, 1))()
+    for i, (kind, v, rho, e) in enumerate(boxes):
+        ext[i] = e
+        tab[i].kind = kind
+        tab[i].v[0], tab[i].v[1], tab[i].v[2] = v
+        tab[i].rho = rho
+    return ext, tab
+
+
+class Domain:
+    """Python mirror of lbm::Domain<M> + BGKCollision<M>(tau) backed by one GPU slab.
+
+    Domain(Q, xl, yl, zl, tau)                        whole domain
+    Domain(Q, xl, yl, zl_global, tau, z_first=, zl_local=)   one z-slab
+    """
+
+    def __init__(self, Q, xl, yl, zl, tau, device=-1, z_first=None, zl_local=None, exact=False):
+        self._h = _H()
+        self.Q, self.xl, self.yl, self.zl_global, self.tau = Q, xl, yl, zl, tau
+        if z_first is None:
+            self.z_first, self.zl = 1, zl
+            _check(lib.lbm_b200_create(C.byref(self._h), Q, xl, yl, zl, tau, device))
+        else:
+            self.z_first, self.zl = z_first, zl_local
+            _check(lib.lbm_b200_create_slab(C.byref(self._h), Q, xl, yl, zl, z_first, zl_local, tau, device))
+        self.ncell = (xl + 2) * (yl + 2) * (self.zl + 2)
+        if exact:
+            self.set_arithmetic(EXACT)
+
+    # -- life cycle
+    def close(self):
+        if self._h:
+            lib.lbm_b200_destroy(self._h)
+            self._h = _H()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- configuration
+    def set_arithmetic(self, mode):
+        _check(lib.lbm_b200_set_arithmetic(self._h, mode))
+
+    def set_stream(self, cuda_stream):
+        _check(lib.lbm_b200_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_boxes(self, boxes):
+        ext, tab = _boxes_arrays(boxes)
+        _check(lib.lbm_b200_set_boxes(self._h, ext.ctypes.data, C.cast(tab, C.c_void_p), len(boxes)))
+
+    def set_geometry(self, kind, bc_id=None, table=()):
+        kind = np.ascontiguousarray(kind, dtype=np.uint8).reshape(-1)
+        assert kind.size == self.ncell
+        _, tab = _boxes_arrays([(k, v, rho, (0,) * 6) for (k, v, rho) in table])
+        bid = None
+        if bc_id is not None:
+            bid = np.ascontiguousarray(bc_id, dtype=np.uint16).reshape(-1)
+            assert bid.size == self.ncell
+        _check(lib.lbm_b200_set_geometry(self._h, kind.ctypes.data, bid.ctypes.data if bid is not None else None,
+                                         C.cast(tab, C.c_void_p), len(table)))
+
+    def set_fluid_mask(self, mask):
+        m = np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
+        assert m.size == self.xl * self.yl * self.zl
+        _check(lib.lbm_b200_set_fluid_mask(self._h, m.ctypes.data))
+
+    def kind(self):
+        k = np.empty(self.ncell, dtype=np.uint8)
+        _check(lib.lbm_b200_get_kind(self._h, k.ctypes.data))
+        return k
+
+    # -- state
+    def upload(self, f, layout=AOS, field=COLLIDE_FIELD):
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        assert f.size == self.ncell * self.Q
+        _check(lib.lbm_b200_upload_populations(self._h, f.ctypes.data, layout, field))
+
+    def download(self, layout=AOS, field=COLLIDE_FIELD, out=None):
+        shape = (self.ncell, self.Q) if layout == AOS else (self.Q, self.ncell)
+        f = out if out is not None else np.empty(shape)
+        _check(lib.lbm_b200_download_populations(self._h, f.ctypes.data, layout, field))
+        return f
+
+    def init_equilibrium(self, rho, u):
+        rho = np.ascontiguousarray(rho, dtype=np.float64).reshape(-1)
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+        assert rho.size == self.ncell and u.size == 3 * self.ncell
+        _check(lib.lbm_b200_init_equilibrium(self._h, rho.ctypes.data, u.ctypes.data))
+
+    # -- hot path
+    def step(self, n=1):
+        _check(lib.lbm_b200_step(self._h, n))
+
+    def sync(self):
+        _check(lib.lbm_b200_sync(self._h))
+
+    def elapsed_ms(self):
+        ms = C.c_double()
+        _check(lib.lbm_b200_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        _check(lib.lbm_b200_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def steps_done(self):
+        return lib.lbm_b200_steps_done(self._h)
+
+    # -- read-out
+    def macroscopic(self, rho=None, u=None):
+        """(rho[zl,yl,xl], u[zl,yl,xl,3]) of the interior cells, io/vtk.hpp:62-73 order."""
+        if rho is None:
+            rho = np.empty((self.zl, self.yl, self.xl))
+        if u is None:
+            u = np.empty((self.zl, self.yl, self.xl, 3))
+        _check(lib.lbm_b200_macroscopic(self._h, rho.ctypes.data, u.ctypes.data))
+        return rho, u
+
+    def diagnostics(self):
+        m, k, um = C.c_double(), C.c_double(), C.c_double()
+        _check(lib.lbm_b200_diagnostics(self._h, C.byref(m), C.byref(k), C.byref(um)))
+        return m.value, k.value, um.value
+
+    # -- slabs
+    def halo_layout(self):
+        n, b = C.c_int(), C.c_size_t()
+        _check(lib.lbm_b200_halo_layout(self._h, C.byref(n), C.byref(b)))
+        return n.value, b.value
+
+    def halo_plane(self, buffer, side, k, recv):
+        p = C.c_void_p()
+        _check(lib.lbm_b200_halo_plane(self._h, buffer, side, k, int(recv), C.byref(p)))
+        return p.value
+
+    def dst_buffer(self):
+        return lib.lbm_b200_dst_buffer(self._h)
+
+    def step_edges(self):
+        _check(lib.lbm_b200_step_edges(self._h))
+
+    def step_interior(self):
+        _check(lib.lbm_b200_step_interior(self._h))
+
+    def step_finish(self):
+        _check(lib.lbm_b200_step_finish(self._h))
+
+    def export(self):
+        blob = C.create_string_buffer(EXPORT_BYTES)
+        _check(lib.lbm_b200_export(self._h, blob))
+        return blob.raw
+
+    def connect(self, side, blob):
+        _check(lib.lbm_b200_connect(self._h, side, C.c_char_p(blob)))
+
+    def connect_local(self, side, other):
+        _check(lib.lbm_b200_connect_local(self._h, side, other._h))

@@ -1,0 +1,885 @@
+// engine.cu -- host side of the C ABI declared in include/lbm_b200.h.
+//
+// One handle = one Domain (domain.h:12-19) or one z-slab of it, resident on one
+// B200.  The reference's stream(); swap(); collide(); (src/main.cpp:50-52) is a
+// single launch of sweep_kernel per step plus a buffer-index flip.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lbm_b200.h"
+#include "kernels.cuh"
+
+using namespace lbmb200;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(e_ == cudaErrorMemoryAllocation ? LBM_B200_ENOMEM : LBM_B200_ECUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define TRY(expr)                 \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+// host copy of compute_feq (collision.hpp:34-51); this translation unit's host
+// code is built with -ffp-contract=off, so the association below is what runs.
+void feq_host(int Q, double rho, const double* u, double* out)
+{
+    double vel[27 * 3], w[27];
+    lbm_b200_model(Q, vel, w);
+    for (int q = 0; q < Q; ++q) {
+        double c_dot_u = 0.0, u_dot_u = 0.0;
+        for (int d = 0; d < 3; ++d) {
+            c_dot_u += vel[q * 3 + d] * u[d];
+            u_dot_u += u[d] * u[d];
+        }
+        out[q] = w[q] * rho * (1 + c_dot_u / CS2 + (c_dot_u) * (c_dot_u) / TWO_CS4 - u_dot_u / TWO_CS2);
+    }
+}
+
+template <typename F>
+auto dispatch_q(int Q, F&& f)
+{
+    switch (Q) {
+    case 15: return f(std::integral_constant<int, 15>{});
+    case 19: return f(std::integral_constant<int, 19>{});
+    default: return f(std::integral_constant<int, 27>{});
+    }
+}
+
+} // namespace
+
+struct lbm_b200 {
+    int Q = 0;
+    int device = 0;
+    Layout g{};
+    int zl_global = 0;
+    int z_first = 1;           // global index of local plane 1
+    double tau = 1.0;
+    int exact = 0;
+
+    double* f[2] = { nullptr, nullptr };
+    int cur = 0;               // f[cur] is the collide field
+    uint32_t* d_mask = nullptr;
+    uint8_t* d_kind = nullptr;
+    uint16_t* d_bcid = nullptr;
+    BcRec* d_bc = nullptr;
+    int* d_ghost = nullptr;
+    int n_ghost = 0;
+
+    std::vector<uint8_t> h_kind;     // dense, local idx order
+    std::vector<uint16_t> h_bcid;
+    std::vector<lbm_b200_bc> h_bc;
+    bool geom_dirty = true;
+    bool first = true;         // boundary cells hold host-visible (stored) values
+    bool materialized = true;  // boundary cells of f[cur] hold the reference's values
+    int wrap_z = 0;
+
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    bool timed = false;
+    uint64_t steps = 0;
+    uint64_t launches = 0;
+    bool edges_done = false;   // split-phase state
+
+    // direct peer stores: [side]
+    double* peer_f[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   // [side][buffer]
+    long long peer_qstride[2] = { 0, 0 };
+    long long peer_off[2] = { 0, 0 };
+    void* peer_ipc_base[2] = { nullptr, nullptr };
+
+    size_t ncell() const { return (size_t) (g.xl + 2) * (g.yl + 2) * (g.zl + 2); }
+    size_t field_bytes() const { return (size_t) g.qstride * Q * sizeof(double); }
+    size_t map_elems() const { return (size_t) g.qstride; }
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define GUARD(h)                                                                     \
+    if (!(h)) return fail(LBM_B200_EINVAL, "null handle");                           \
+    DeviceGuard guard_((h)->device);                                                 \
+    if (!guard_.ok) return fail(LBM_B200_ECUDA, "cannot select CUDA device %d", (h)->device)
+
+dim3 map_grid(const Layout& g, int nz) { return dim3((g.xl + 2 + 127) / 128, g.yl + 2, nz); }
+
+int fill_weights(lbm_b200* h, int buffer)
+{
+    dispatch_q(h->Q, [&](auto Qc) {
+        fill_weights_kernel<decltype(Qc)::value><<<148 * 8, 256, 0, h->stream>>>(h->f[buffer], h->g.qstride);
+        return 0;
+    });
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// upload maps, boundary table, link mask, ghost-fluid list
+int commit_geometry(lbm_b200* h)
+{
+    if (!h->geom_dirty) return 0;
+    const Layout& g = h->g;
+    const size_t n = h->ncell();
+    // boundary records
+    {
+        std::vector<BcRec> recs(std::max<size_t>(1, h->h_bc.size()));
+        memset(recs.data(), 0, recs.size() * sizeof(BcRec));
+        for (size_t i = 0; i < h->h_bc.size(); ++i) {
+            recs[i].kind = h->h_bc[i].kind;
+            for (int d = 0; d < 3; ++d) recs[i].v[d] = h->h_bc[i].v[d];
+            recs[i].rho = h->h_bc[i].rho;
+            if (recs[i].kind == LBM_B200_INFLOW) feq_host(h->Q, recs[i].rho, recs[i].v, recs[i].feq);
+        }
+        if (h->d_bc) CU(cudaFree(h->d_bc));
+        h->d_bc = nullptr;
+        CU(cudaMalloc(&h->d_bc, recs.size() * sizeof(BcRec)));
+        CU(cudaMemcpyAsync(h->d_bc, recs.data(), recs.size() * sizeof(BcRec), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    // validate + ghost-fluid list + periodic z
+    std::vector<int> ghost;
+    bool periodic_z = false;
+    const int nb = (int) h->h_bc.size();
+    for (int z = 0; z < g.zl + 2; ++z)
+        for (int y = 0; y < g.yl + 2; ++y) {
+            const size_t row = ((size_t) z * (g.yl + 2) + y) * (g.xl + 2);
+            for (int x = 0; x < g.xl + 2; ++x) {
+                const int k = h->h_kind[row + x];
+                if (k >= K_COUNT) return fail(LBM_B200_EINVAL, "cell (%d,%d,%d): unknown kind %d", x, y, z, k);
+                if (k >= K_NOSLIP && k <= K_PRESSURE) {
+                    const int id = h->h_bcid[row + x];
+                    if (id >= nb) return fail(LBM_B200_EINVAL, "cell (%d,%d,%d): bc id %d outside table of %d", x, y, z, id, nb);
+                    if (h->h_bc[id].kind != k)
+                        return fail(LBM_B200_EINVAL, "cell (%d,%d,%d): kind %d but table[%d].kind = %d", x, y, z, k, id, h->h_bc[id].kind);
+                }
+                const bool zshell = (z == 0 && h->z_first == 1) || (z == g.zl + 1 && h->z_first + g.zl - 1 == h->zl_global);
+                const bool shell = x == 0 || x == g.xl + 1 || y == 0 || y == g.yl + 1 || zshell;
+                const bool interior = x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1;
+                if (shell && k == K_FLUID && ((z > 0 && z < g.zl + 1) || zshell)) ghost.push_back(cell_at(g, x, y, z));
+                if (k == K_PERIODIC) {
+                    if (interior) return fail(LBM_B200_EINVAL, "cell (%d,%d,%d): PERIODIC is a ghost-shell kind", x, y, z);
+                    if (z == 0 || z == g.zl + 1) periodic_z = true;
+                }
+                if (!shell && !interior) { /* interface ghost plane of a slab: replica of the neighbour */ }
+            }
+        }
+    if (periodic_z && (h->z_first != 1 || g.zl != h->zl_global))
+        periodic_z = false;   // closed by the slab ring exchange instead
+    h->wrap_z = periodic_z ? 1 : 0;
+    if (!ghost.empty() && g.zl != h->zl_global)
+        return fail(LBM_B200_EINVAL, "%zu ghost-shell cells carry the fluid handler; on a multi-slab domain the "
+                    "whole shell must be covered by boundary conditions", ghost.size());
+
+    // dense -> padded maps through a device staging copy
+    {
+        uint8_t* stage8 = nullptr;
+        uint16_t* stage16 = nullptr;
+        CU(cudaMalloc(&stage8, n));
+        CU(cudaMalloc(&stage16, n * sizeof(uint16_t)));
+        CU(cudaMemcpyAsync(stage8, h->h_kind.data(), n, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(stage16, h->h_bcid.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(h->d_kind, K_NULL, h->map_elems(), h->stream));
+        CU(cudaMemsetAsync(h->d_bcid, 0, h->map_elems() * sizeof(uint16_t), h->stream));
+        scatter_map_kernel<uint8_t><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(stage8, h->d_kind, g, 0);
+        scatter_map_kernel<uint16_t><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(stage16, h->d_bcid, g, 0);
+        CU(cudaMemsetAsync(h->d_mask, 0x80, h->map_elems() * sizeof(uint32_t), h->stream));
+        dispatch_q(h->Q, [&](auto Qc) {
+            build_mask_kernel<decltype(Qc)::value><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->d_kind, h->d_mask, g);
+            return 0;
+        });
+        h->launches += 3;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaFree(stage8));
+        CU(cudaFree(stage16));
+    }
+    if (h->d_ghost) CU(cudaFree(h->d_ghost));
+    h->d_ghost = nullptr;
+    h->n_ghost = (int) ghost.size();
+    if (h->n_ghost) {
+        CU(cudaMalloc(&h->d_ghost, ghost.size() * sizeof(int)));
+        CU(cudaMemcpy(h->d_ghost, ghost.data(), ghost.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    h->geom_dirty = false;
+    return 0;
+}
+
+int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers)
+{
+    if (nz <= 0) return 0;
+    const Layout& g = h->g;
+    SweepParams p{};
+    p.src = h->f[h->cur];
+    p.dst = h->f[1 - h->cur];
+    p.mask = h->d_mask;
+    p.kind = h->d_kind;
+    p.bcid = h->d_bcid;
+    p.bc = h->d_bc;
+    p.g = g;
+    p.z0 = z0;
+    int shift = 7;                       // 128 threads along x ...
+    while (shift > 5 && (1 << (shift - 1)) >= g.xl) --shift;   // ... unless the row is short
+    p.bx_shift = shift;
+    p.first = h->first ? 1 : 0;
+    p.wrap_z = h->wrap_z;
+    p.tau = h->tau;
+    p.omega = 1.0 / h->tau;
+    if (with_peers) {
+        const int dstbuf = 1 - h->cur;
+        p.up_dst = h->peer_f[LBM_B200_UP][dstbuf];
+        p.up_qstride = h->peer_qstride[LBM_B200_UP];
+        p.up_off = h->peer_off[LBM_B200_UP];
+        p.dn_dst = h->peer_f[LBM_B200_DOWN][dstbuf];
+        p.dn_qstride = h->peer_qstride[LBM_B200_DOWN];
+        p.dn_off = h->peer_off[LBM_B200_DOWN];
+    }
+    const int bx = 1 << shift, by = 128 >> shift;
+    dim3 grid((g.xl + bx - 1) / bx, (g.yl + by - 1) / by, nz);
+    dispatch_q(h->Q, [&](auto Qc) {
+        constexpr int Q = decltype(Qc)::value;
+        if (h->exact) sweep_kernel<Q, true><<<grid, 128, 0, h->stream>>>(p);
+        else sweep_kernel<Q, false><<<grid, 128, 0, h->stream>>>(p);
+        return 0;
+    });
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_ghost(lbm_b200* h)
+{
+    if (!h->n_ghost) return 0;
+    double* field = h->f[1 - h->cur];
+    dispatch_q(h->Q, [&](auto Qc) {
+        constexpr int Q = decltype(Qc)::value;
+        const int blocks = (h->n_ghost + 127) / 128;
+        if (h->exact) ghost_fluid_kernel<Q, true><<<blocks, 128, 0, h->stream>>>(field, h->g.qstride, h->d_ghost, h->n_ghost, h->tau, 1.0 / h->tau);
+        else ghost_fluid_kernel<Q, false><<<blocks, 128, 0, h->stream>>>(field, h->g.qstride, h->d_ghost, h->n_ghost, h->tau, 1.0 / h->tau);
+        return 0;
+    });
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+void finish_step(lbm_b200* h)
+{
+    h->cur = 1 - h->cur;      // Domain::swap, domain.hpp:169-172
+    h->first = false;
+    h->materialized = false;
+    h->steps++;
+}
+
+int materialize(lbm_b200* h)
+{
+    TRY(commit_geometry(h));
+    if (h->materialized) return 0;
+    const Layout& g = h->g;
+    dispatch_q(h->Q, [&](auto Qc) {
+        constexpr int Q = decltype(Qc)::value;
+        if (h->exact) materialize_kernel<Q, true><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, h->d_bcid, h->d_bc, g);
+        else materialize_kernel<Q, false><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, h->d_bcid, h->d_bc, g);
+        return 0;
+    });
+    h->launches++;
+    CU(cudaGetLastError());
+    h->materialized = true;
+    return 0;
+}
+
+int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl_global, uint64_t z_first,
+                  uint64_t zl_local, double tau, int device)
+{
+    if (!out) return fail(LBM_B200_EINVAL, "null output pointer");
+    *out = nullptr;
+    if (Q != 15 && Q != 19 && Q != 27) return fail(LBM_B200_EINVAL, "Q must be 15, 19 or 27 (got %d)", Q);
+    if (xl == 0 || yl == 0 || zl_global == 0 || zl_local == 0)
+        return fail(LBM_B200_EINVAL, "domain lengths must be positive");
+    if (z_first < 1 || z_first + zl_local - 1 > zl_global)
+        return fail(LBM_B200_EINVAL, "slab [%llu, %llu] outside 1..%llu", (unsigned long long) z_first,
+                    (unsigned long long) (z_first + zl_local - 1), (unsigned long long) zl_global);
+    if (!(tau > 0.0)) return fail(LBM_B200_EINVAL, "tau must be positive (got %g)", tau);
+    if (yl + 2 > 65535 || zl_local + 2 > 65535) return fail(LBM_B200_EINVAL, "yl and zl are limited to 65533");
+    const uint64_t P = (xl + 2 + 15) / 16 * 16;
+    const uint64_t plane = P * (yl + 2);
+    const uint64_t qstride = plane * (zl_local + 2) + 16;
+    if (qstride >= (1ull << 31)) return fail(LBM_B200_EINVAL, "slab too large: %llu padded cells per population (limit 2^31)", (unsigned long long) qstride);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(LBM_B200_ECUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return fail(LBM_B200_ECUDA, "cudaGetDevice failed");
+    }
+    if (device >= ndev) return fail(LBM_B200_EINVAL, "device %d out of range (%d visible)", device, ndev);
+
+    lbm_b200* h = new lbm_b200();
+    h->Q = Q;
+    h->device = device;
+    h->g.xl = (int) xl; h->g.yl = (int) yl; h->g.zl = (int) zl_local;
+    h->g.P = (int) P; h->g.plane = (int) plane; h->g.qstride = (long long) qstride;
+    h->zl_global = (int) zl_global;
+    h->z_first = (int) z_first;
+    h->tau = tau;
+    *out = h;   // so that the caller can destroy on failure below
+    DeviceGuard guard(device);
+    if (!guard.ok) { lbm_b200_destroy(h); *out = nullptr; return fail(LBM_B200_ECUDA, "cannot select CUDA device %d", device); }
+
+    auto bail = [&](int rc) { std::string keep = g_error; lbm_b200_destroy(h); *out = nullptr; g_error = keep; return rc; };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        fail(e_ == cudaErrorMemoryAllocation ? LBM_B200_ENOMEM : LBM_B200_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+        cudaGetLastError(); return bail(e_ == cudaErrorMemoryAllocation ? LBM_B200_ENOMEM : LBM_B200_ECUDA); } } while (0)
+    CUB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CUB(cudaEventCreate(&h->ev_a));
+    CUB(cudaEventCreate(&h->ev_b));
+    // one allocation for both lattices: a neighbour maps it with a single IPC handle
+    CUB(cudaMalloc(&h->f[0], 2 * h->field_bytes()));
+    h->f[1] = h->f[0] + (size_t) h->g.qstride * Q;
+    CUB(cudaMalloc(&h->d_mask, h->map_elems() * sizeof(uint32_t)));
+    CUB(cudaMalloc(&h->d_kind, h->map_elems()));
+    CUB(cudaMalloc(&h->d_bcid, h->map_elems() * sizeof(uint16_t)));
+#undef CUB
+    h->h_kind.assign(h->ncell(), (uint8_t) LBM_B200_FLUID);   // domain.hpp:87-93
+    h->h_bcid.assign(h->ncell(), 0);
+    if (fill_weights(h, 0) != 0 || fill_weights(h, 1) != 0) return bail(LBM_B200_ECUDA);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { fail(LBM_B200_ECUDA, "initial fill failed"); return bail(LBM_B200_ECUDA); }
+    return 0;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* lbm_b200_last_error(void) { return g_error.c_str(); }
+int lbm_b200_abi_version(void) { return LBM_B200_ABI_VERSION; }
+
+int lbm_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int lbm_b200_model(int Q, double* velocities, double* weights)
+{
+    if (Q != 15 && Q != 19 && Q != 27) return fail(LBM_B200_EINVAL, "Q must be 15, 19 or 27 (got %d)", Q);
+    dispatch_q(Q, [&](auto Qc) {
+        using L = Lattice<decltype(Qc)::value>;
+        for (int q = 0; q < Q; ++q) {
+            if (velocities) { velocities[3 * q] = L::cx(q); velocities[3 * q + 1] = L::cy(q); velocities[3 * q + 2] = L::cz(q); }
+            if (weights) weights[q] = L::w(q);
+        }
+        return 0;
+    });
+    return 0;
+}
+int lbm_b200_model_inv(int Q, int q) { return Q - 1 - q; }
+int lbm_b200_model_velocity_index(int Q, int u, int v, int w)
+{
+    if (Q != 15 && Q != 19 && Q != 27) return fail(LBM_B200_EINVAL, "Q must be 15, 19 or 27 (got %d)", Q);
+    if (u < -1 || u > 1 || v < -1 || v > 1 || w < -1 || w > 1) return fail(LBM_B200_EINVAL, "components must be -1, 0 or 1");
+    return dispatch_q(Q, [&](auto Qc) { return Lattice<decltype(Qc)::value>::index_of(u, v, w); });
+}
+
+int lbm_b200_create(lbm_b200_t** h, int Q, uint64_t xl, uint64_t yl, uint64_t zl, double tau, int device)
+{
+    return create_common(h, Q, xl, yl, zl, 1, zl, tau, device);
+}
+int lbm_b200_create_slab(lbm_b200_t** h, int Q, uint64_t xl, uint64_t yl, uint64_t zl_global, uint64_t z_first,
+                         uint64_t zl_local, double tau, int device)
+{
+    return create_common(h, Q, xl, yl, zl_global, z_first, zl_local, tau, device);
+}
+
+int lbm_b200_destroy(lbm_b200_t* h)
+{
+    if (!h) return 0;
+    DeviceGuard guard(h->device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    for (int s = 0; s < 2; ++s)
+        if (h->peer_ipc_base[s]) cudaIpcCloseMemHandle(h->peer_ipc_base[s]);
+    if (h->f[0]) cudaFree(h->f[0]);
+    if (h->d_mask) cudaFree(h->d_mask);
+    if (h->d_kind) cudaFree(h->d_kind);
+    if (h->d_bcid) cudaFree(h->d_bcid);
+    if (h->d_bc) cudaFree(h->d_bc);
+    if (h->d_ghost) cudaFree(h->d_ghost);
+    if (h->ev_a) cudaEventDestroy(h->ev_a);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    cudaGetLastError();
+    delete h;
+    return 0;
+}
+
+int lbm_b200_set_arithmetic(lbm_b200_t* h, int mode)
+{
+    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    if (mode != LBM_B200_FAST && mode != LBM_B200_EXACT) return fail(LBM_B200_EINVAL, "unknown arithmetic mode %d", mode);
+    h->exact = mode == LBM_B200_EXACT;
+    return 0;
+}
+int lbm_b200_set_tau(lbm_b200_t* h, double tau)
+{
+    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    if (!(tau > 0.0)) return fail(LBM_B200_EINVAL, "tau must be positive (got %g)", tau);
+    h->tau = tau;
+    return 0;
+}
+int lbm_b200_set_stream(lbm_b200_t* h, void* cuda_stream)
+{
+    GUARD(h);
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t) cuda_stream : h->own_stream;
+    return 0;
+}
+
+int lbm_b200_set_geometry(lbm_b200_t* h, const uint8_t* kind, const uint16_t* bc_id, const lbm_b200_bc* table, int n_table)
+{
+    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    if (!kind) return fail(LBM_B200_EINVAL, "kind map is null");
+    if (n_table < 0 || n_table > 65535 || (n_table > 0 && !table)) return fail(LBM_B200_EINVAL, "bad boundary table");
+    if (!bc_id && n_table > 1) return fail(LBM_B200_EINVAL, "bc_id map required for a table of %d handlers", n_table);
+    const size_t n = h->ncell();
+    h->h_kind.assign(kind, kind + n);
+    if (bc_id) h->h_bcid.assign(bc_id, bc_id + n);
+    else h->h_bcid.assign(n, 0);
+    h->h_bc.assign(table, table + n_table);
+    h->geom_dirty = true;
+    h->materialized = false;
+    return 0;
+}
+
+int lbm_b200_set_boxes(lbm_b200_t* h, const uint64_t* boxes6, const lbm_b200_bc* table, int n)
+{
+    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    if (n < 0 || (n > 0 && (!boxes6 || !table))) return fail(LBM_B200_EINVAL, "bad box list");
+    const Layout& g = h->g;
+    for (int b = 0; b < n; ++b) {
+        const uint64_t* e = boxes6 + 6 * b;
+        // the reference asserts these (domain.hpp:180-181)
+        if (!(e[1] >= e[0] && e[3] >= e[2] && e[5] >= e[4]))
+            return fail(LBM_B200_EINVAL, "box %d: end before begin", b);
+        if (!(e[1] < (uint64_t) g.xl + 2 && e[3] < (uint64_t) g.yl + 2 && e[5] < (uint64_t) h->zl_global + 2))
+            return fail(LBM_B200_EINVAL, "box %d: extent outside the domain", b);
+        const int k = table[b].kind;
+        if (!((k >= K_NOSLIP && k <= K_PRESSURE) || k == K_PARALLEL || k == K_PERIODIC || k == K_NULL || k == K_FLUID))
+            return fail(LBM_B200_EINVAL, "box %d: unknown kind %d", b, k);
+        if (h->h_bc.size() >= 65535) return fail(LBM_B200_EINVAL, "more than 65535 boundary handlers");
+        const uint16_t id = (uint16_t) h->h_bc.size();
+        h->h_bc.push_back(table[b]);
+        const long long zoff = h->z_first - 1;   // local z = global z - zoff
+        const long long lz0 = std::max<long long>((long long) e[4] - zoff, 0);
+        const long long lz1 = std::min<long long>((long long) e[5] - zoff, g.zl + 1);
+        for (long long z = lz0; z <= lz1; ++z)
+            for (uint64_t y = e[2]; y <= e[3]; ++y) {
+                const size_t row = ((size_t) z * (g.yl + 2) + y) * (g.xl + 2);
+                for (uint64_t x = e[0]; x <= e[1]; ++x) {
+                    h->h_kind[row + x] = (uint8_t) k;
+                    h->h_bcid[row + x] = id;
+                }
+            }
+    }
+    h->geom_dirty = true;
+    h->materialized = false;
+    return 0;
+}
+
+int lbm_b200_set_fluid_mask(lbm_b200_t* h, const uint8_t* mask)
+{
+    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    if (!mask) return fail(LBM_B200_EINVAL, "mask is null");
+    if (h->h_bc.size() >= 65535) return fail(LBM_B200_EINVAL, "more than 65535 boundary handlers");
+    const Layout& g = h->g;
+    lbm_b200_bc solid{};
+    solid.kind = LBM_B200_NOSLIP;
+    solid.rho = 1.0;
+    const uint16_t id = (uint16_t) h->h_bc.size();
+    h->h_bc.push_back(solid);
+    size_t i = 0;
+    for (int z = 1; z < g.zl + 1; ++z)
+        for (int y = 1; y < g.yl + 1; ++y) {
+            const size_t row = ((size_t) z * (g.yl + 2) + y) * (g.xl + 2);
+            for (int x = 1; x < g.xl + 1; ++x, ++i)
+                if (!mask[i]) {
+                    h->h_kind[row + x] = LBM_B200_NOSLIP;
+                    h->h_bcid[row + x] = id;
+                }
+        }
+    h->geom_dirty = true;
+    h->materialized = false;
+    return 0;
+}
+
+int lbm_b200_get_kind(lbm_b200_t* h, uint8_t* kind)
+{
+    if (!h || !kind) return fail(LBM_B200_EINVAL, "null argument");
+    memcpy(kind, h->h_kind.data(), h->ncell());
+    return 0;
+}
+
+// ---- state ------------------------------------------------------------------
+static int transfer_populations(lbm_b200* h, double* host, int layout, int field, bool upload)
+{
+    if (!host) return fail(LBM_B200_EINVAL, "population array is null");
+    if (field != LBM_B200_COLLIDE_FIELD && field != LBM_B200_STREAM_FIELD) return fail(LBM_B200_EINVAL, "unknown field %d", field);
+    const Layout& g = h->g;
+    double* dev = h->f[field == LBM_B200_COLLIDE_FIELD ? h->cur : 1 - h->cur];
+    const int Q = h->Q;
+    if (layout == LBM_B200_SOA) {
+        const size_t n = h->ncell();
+        for (int q = 0; q < Q; ++q) {
+            double* d = dev + (size_t) q * g.qstride + X_SHIFT;
+            double* s = host + (size_t) q * n;
+            const size_t rows = (size_t) (g.yl + 2) * (g.zl + 2);
+            if (upload) CU(cudaMemcpy2DAsync(d, g.P * sizeof(double), s, (g.xl + 2) * sizeof(double), (g.xl + 2) * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream));
+            else CU(cudaMemcpy2DAsync(s, (g.xl + 2) * sizeof(double), d, g.P * sizeof(double), (g.xl + 2) * sizeof(double), rows, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (layout != LBM_B200_AOS) return fail(LBM_B200_EINVAL, "unknown layout %d", layout);
+    // chunks of z planes through a device staging buffer of at most ~256 MB
+    const size_t plane_vals = (size_t) (g.xl + 2) * (g.yl + 2) * Q;
+    int chunk = (int) std::max<size_t>(1, ((size_t) 256 << 20) / (plane_vals * sizeof(double)));
+    chunk = std::min(chunk, g.zl + 2);
+    double* stage = nullptr;
+    CU(cudaMalloc(&stage, plane_vals * chunk * sizeof(double)));
+    int rc = 0;
+    for (int z0 = 0; z0 < g.zl + 2 && rc == 0; z0 += chunk) {
+        const int nz = std::min(chunk, g.zl + 2 - z0);
+        double* hp = host + plane_vals * z0;
+        cudaError_t e = cudaSuccess;
+        if (upload) e = cudaMemcpyAsync(stage, hp, plane_vals * nz * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) {
+            dispatch_q(Q, [&](auto Qc) {
+                constexpr int QQ = decltype(Qc)::value;
+                if (upload) transpose_aos_kernel<QQ, true><<<map_grid(g, nz), 128, 0, h->stream>>>(stage, dev, g, z0);
+                else transpose_aos_kernel<QQ, false><<<map_grid(g, nz), 128, 0, h->stream>>>(stage, dev, g, z0);
+                return 0;
+            });
+            h->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && !upload) e = cudaMemcpyAsync(hp, stage, plane_vals * nz * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(LBM_B200_ECUDA, "population transfer failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(stage);
+    return rc;
+}
+
+int lbm_b200_upload_populations(lbm_b200_t* h, const double* f, int layout, int field)
+{
+    GUARD(h);
+    TRY(transfer_populations(h, const_cast<double*>(f), layout, field, true));
+    if (field == LBM_B200_COLLIDE_FIELD) {
+        h->first = true;          // boundary cells now hold host-chosen values
+        h->materialized = true;
+    }
+    return 0;
+}
+
+int lbm_b200_download_populations(lbm_b200_t* h, double* f, int layout, int field)
+{
+    GUARD(h);
+    if (field == LBM_B200_COLLIDE_FIELD) TRY(materialize(h));
+    return transfer_populations(h, f, layout, field, false);
+}
+
+int lbm_b200_init_equilibrium(lbm_b200_t* h, const double* rho, const double* u)
+{
+    GUARD(h);
+    if (!rho || !u) return fail(LBM_B200_EINVAL, "rho / u array is null");
+    const Layout& g = h->g;
+    const size_t plane_cells = (size_t) (g.xl + 2) * (g.yl + 2);
+    int chunk = (int) std::max<size_t>(1, ((size_t) 256 << 20) / (plane_cells * 4 * sizeof(double)));
+    chunk = std::min(chunk, g.zl + 2);
+    double *d_rho = nullptr, *d_u = nullptr;
+    CU(cudaMalloc(&d_rho, plane_cells * chunk * sizeof(double)));
+    if (cudaMalloc(&d_u, plane_cells * chunk * 3 * sizeof(double)) != cudaSuccess) { cudaFree(d_rho); cudaGetLastError(); return fail(LBM_B200_ENOMEM, "staging allocation failed"); }
+    int rc = 0;
+    for (int z0 = 0; z0 < g.zl + 2 && rc == 0; z0 += chunk) {
+        const int nz = std::min(chunk, g.zl + 2 - z0);
+        cudaError_t e = cudaMemcpyAsync(d_rho, rho + plane_cells * z0, plane_cells * nz * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, u + plane_cells * z0 * 3, plane_cells * nz * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) {
+            dispatch_q(h->Q, [&](auto Qc) {
+                equilibrium_kernel<decltype(Qc)::value><<<map_grid(g, nz), 128, 0, h->stream>>>(d_rho, d_u, h->f[h->cur], g, z0);
+                return 0;
+            });
+            h->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(LBM_B200_ECUDA, "equilibrium initialisation failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_rho);
+    cudaFree(d_u);
+    if (rc == 0) { h->first = true; h->materialized = true; }
+    return rc;
+}
+
+// ---- hot path ---------------------------------------------------------------
+int lbm_b200_step(lbm_b200_t* h, uint64_t n_steps)
+{
+    GUARD(h);
+    if (h->edges_done) return fail(LBM_B200_ESTATE, "a split-phase step is in flight");
+    TRY(commit_geometry(h));
+    CU(cudaEventRecord(h->ev_a, h->stream));
+    for (uint64_t s = 0; s < n_steps; ++s) {
+        TRY(launch_sweep(h, 1, h->g.zl, true));
+        TRY(launch_ghost(h));
+        finish_step(h);
+    }
+    CU(cudaEventRecord(h->ev_b, h->stream));
+    h->timed = true;
+    return 0;
+}
+
+int lbm_b200_sync(lbm_b200_t* h)
+{
+    GUARD(h);
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lbm_b200_elapsed_ms(lbm_b200_t* h, double* ms)
+{
+    GUARD(h);
+    if (!ms) return fail(LBM_B200_EINVAL, "null output pointer");
+    if (!h->timed) return fail(LBM_B200_ESTATE, "no step has been timed yet");
+    CU(cudaEventSynchronize(h->ev_b));
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, h->ev_a, h->ev_b));
+    *ms = t;
+    return 0;
+}
+
+int lbm_b200_launch_count(lbm_b200_t* h, uint64_t* n)
+{
+    if (!h || !n) return fail(LBM_B200_EINVAL, "null argument");
+    *n = h->launches;
+    return 0;
+}
+uint64_t lbm_b200_steps_done(lbm_b200_t* h) { return h ? h->steps : 0; }
+
+// ---- read-out -----------------------------------------------------------------
+int lbm_b200_macroscopic(lbm_b200_t* h, double* rho, double* u)
+{
+    GUARD(h);
+    TRY(materialize(h));
+    const Layout& g = h->g;
+    const size_t n = (size_t) g.xl * g.yl * g.zl;
+    double *d_rho = nullptr, *d_u = nullptr;
+    if (rho) CU(cudaMalloc(&d_rho, n * sizeof(double)));
+    if (u && cudaMalloc(&d_u, 3 * n * sizeof(double)) != cudaSuccess) { cudaFree(d_rho); cudaGetLastError(); return fail(LBM_B200_ENOMEM, "output staging allocation failed"); }
+    dim3 grid((g.xl + 127) / 128, g.yl, g.zl);
+    dispatch_q(h->Q, [&](auto Qc) {
+        macroscopic_kernel<decltype(Qc)::value><<<grid, 128, 0, h->stream>>>(h->f[h->cur], g, d_rho, d_u);
+        return 0;
+    });
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && rho) e = cudaMemcpyAsync(rho, d_rho, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && u) e = cudaMemcpyAsync(u, d_u, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_rho);
+    cudaFree(d_u);
+    if (e != cudaSuccess) return fail(LBM_B200_ECUDA, "macroscopic read-out failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int lbm_b200_diagnostics(lbm_b200_t* h, double* mass, double* kinetic, double* umax)
+{
+    GUARD(h);
+    TRY(commit_geometry(h));
+    const Layout& g = h->g;
+    dim3 grid((g.xl + 127) / 128, g.yl, g.zl);
+    const size_t nblk = (size_t) grid.x * grid.y * grid.z;
+    double* d_part = nullptr;
+    CU(cudaMalloc(&d_part, nblk * 3 * sizeof(double)));
+    dispatch_q(h->Q, [&](auto Qc) {
+        diagnostics_kernel<decltype(Qc)::value><<<grid, 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, g, d_part);
+        return 0;
+    });
+    h->launches++;
+    std::vector<double> part(nblk * 3);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d_part, nblk * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_part);
+    if (e != cudaSuccess) return fail(LBM_B200_ECUDA, "diagnostics failed: %s", cudaGetErrorString(e));
+    double m = 0.0, k = 0.0, um = 0.0;
+    for (size_t b = 0; b < nblk; ++b) { m += part[3 * b]; k += part[3 * b + 1]; um = std::max(um, part[3 * b + 2]); }
+    if (mass) *mass = m;
+    if (kinetic) *kinetic = k;
+    if (umax) *umax = std::sqrt(um);
+    return 0;
+}
+
+// ---- multi-GPU z-slabs ----------------------------------------------------------
+int lbm_b200_halo_layout(lbm_b200_t* h, int* n_q, size_t* bytes)
+{
+    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    const int n = dispatch_q(h->Q, [&](auto Qc) { return Lattice<decltype(Qc)::value>::n_up(); });
+    if (n_q) *n_q = n;
+    if (bytes) *bytes = (size_t) h->g.plane * sizeof(double);
+    return 0;
+}
+
+int lbm_b200_halo_plane(lbm_b200_t* h, int buffer, int side, int k, int recv, void** ptr)
+{
+    if (!h || !ptr) return fail(LBM_B200_EINVAL, "null argument");
+    if (buffer < 0 || buffer > 1 || side < 0 || side > 1) return fail(LBM_B200_EINVAL, "bad buffer/side");
+    // the k-th population with c_z = +1 (side UP sends those; side DOWN receives them) or -1
+    const int want_send = side == LBM_B200_UP ? 1 : -1;
+    const int want = recv ? -want_send : want_send;
+    int q_found = -1;
+    dispatch_q(h->Q, [&](auto Qc) {
+        using L = Lattice<decltype(Qc)::value>;
+        int c = 0;
+        for (int q = 0; q < h->Q; ++q)
+            if (L::cz(q) == want) { if (c == k) q_found = q; ++c; }
+        return 0;
+    });
+    if (q_found < 0) return fail(LBM_B200_EINVAL, "halo population index %d out of range", k);
+    const Layout& g = h->g;
+    int z;
+    if (side == LBM_B200_UP) z = recv ? g.zl + 1 : g.zl;
+    else z = recv ? 0 : 1;
+    *ptr = h->f[buffer] + (size_t) q_found * g.qstride + (size_t) z * g.plane;
+    return 0;
+}
+
+int lbm_b200_dst_buffer(lbm_b200_t* h) { return h ? 1 - h->cur : -1; }
+
+int lbm_b200_step_edges(lbm_b200_t* h)
+{
+    GUARD(h);
+    if (h->edges_done) return fail(LBM_B200_ESTATE, "step_edges called twice");
+    TRY(commit_geometry(h));
+    TRY(launch_sweep(h, 1, 1, true));
+    if (h->g.zl > 1) TRY(launch_sweep(h, h->g.zl, 1, true));
+    h->edges_done = true;
+    return 0;
+}
+int lbm_b200_step_interior(lbm_b200_t* h)
+{
+    GUARD(h);
+    if (!h->edges_done) return fail(LBM_B200_ESTATE, "step_interior before step_edges");
+    TRY(launch_sweep(h, 2, h->g.zl - 2, true));
+    TRY(launch_ghost(h));
+    return 0;
+}
+int lbm_b200_step_finish(lbm_b200_t* h)
+{
+    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    if (!h->edges_done) return fail(LBM_B200_ESTATE, "step_finish before step_edges");
+    h->edges_done = false;
+    finish_step(h);
+    return 0;
+}
+
+int lbm_b200_export(lbm_b200_t* h, void* blob)
+{
+    GUARD(h);
+    if (!blob) return fail(LBM_B200_EINVAL, "null blob");
+    memset(blob, 0, LBM_B200_EXPORT_BYTES);
+    unsigned char* p = (unsigned char*) blob;
+    cudaIpcMemHandle_t mh;
+    CU(cudaIpcGetMemHandle(&mh, h->f[0]));
+    static_assert(sizeof(mh) == 64, "CUDA IPC handle size");
+    memcpy(p, &mh, 64);
+    long long meta[4] = { h->g.qstride, h->g.plane, h->g.zl, h->Q };
+    memcpy(p + 64, meta, sizeof meta);
+    return 0;
+}
+
+static int connect_common(lbm_b200* h, int side, double* base, long long qstride, long long plane, long long zl, long long Q)
+{
+    if (Q != h->Q || plane != h->g.plane) return fail(LBM_B200_EINVAL, "neighbour slab has a different lattice or x-y shape");
+    h->peer_f[side][0] = base;
+    h->peer_f[side][1] = base + (size_t) qstride * Q;
+    h->peer_qstride[side] = qstride;
+    // my top plane feeds the upper neighbour's ghost plane 0; my bottom plane the
+    // lower neighbour's ghost plane zl_nb+1
+    h->peer_off[side] = side == LBM_B200_UP ? 0 : (zl + 1) * plane;
+    return 0;
+}
+
+int lbm_b200_connect(lbm_b200_t* h, int side, const void* blob)
+{
+    GUARD(h);
+    if (side < 0 || side > 1 || !blob) return fail(LBM_B200_EINVAL, "bad side / blob");
+    const unsigned char* p = (const unsigned char*) blob;
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, p, 64);
+    long long meta[4];
+    memcpy(meta, p + 64, sizeof meta);
+    void* base = nullptr;
+    CU(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_ipc_base[side] = base;
+    return connect_common(h, side, (double*) base, meta[0], meta[1], meta[2], meta[3]);
+}
+
+int lbm_b200_connect_local(lbm_b200_t* h, int side, lbm_b200_t* nb)
+{
+    GUARD(h);
+    if (side < 0 || side > 1 || !nb) return fail(LBM_B200_EINVAL, "bad side / neighbour");
+    if (nb->device != h->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, h->device, nb->device));
+        if (!can) return fail(LBM_B200_ECUDA, "device %d cannot access device %d", h->device, nb->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(LBM_B200_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    return connect_common(h, side, nb->f[0], nb->g.qstride, nb->g.plane, nb->g.zl, nb->Q);
+}
+
+} // extern "C"

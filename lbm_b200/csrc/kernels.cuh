@@ -1,0 +1,580 @@
+// kernels.cuh -- sm_100a device code of the lattice-Boltzmann sweep.
+//
+//   K1  sweep_kernel        fused pull-stream + BGK + link-wise boundaries
+//                           (Domain::stream domain.hpp:116-141, Domain::collide
+//                           :144-166, BGKCollision::collide collision.hpp:61-70,
+//                           boundary.hpp:15-214)
+//   K1g ghost_fluid_kernel  in-place BGK of ghost-shell cells left "fluid"
+//                           (domain.hpp:147-155 loops 0..l+1)
+//   K2  materialize_kernel  reference-style boundary pass (domain.hpp:157-165),
+//                           run only before populations are read back
+//   K3  macroscopic_kernel  density / velocity read-out (io/vtk.hpp:62-73)
+//   K5  init / layout / mask kernels
+//
+// Data layout (HBM): structure of arrays  f[buffer][q][z][y][x]  with rows padded
+// to P = roundup(xl+2,16) doubles and shifted by 15 elements so that interior
+// x = 1 starts a 128-byte line.  A row's last ghost element (x = xl+1) spills
+// into element 0 of the next row's padding, which that row never uses.
+#pragma once
+#include <cstdint>
+#include "lattice.cuh"
+
+namespace lbmb200 {
+
+enum : int {
+    K_FLUID = 0, K_NOSLIP = 1, K_MOVINGWALL = 2, K_FREESLIP = 3, K_OUTFLOW = 4,
+    K_INFLOW = 5, K_PRESSURE = 6, K_NULL = 7, K_PARALLEL = 8, K_PERIODIC = 9, K_COUNT = 10
+};
+
+constexpr uint32_t MASK_SKIP = 0x80000000u;   // not an interior fluid cell
+constexpr int X_SHIFT = 15;                   // element offset of x = 0 inside a row
+
+struct BcRec {          // one boundary handler object, device copy
+    int kind;
+    int pad;
+    double v[3];
+    double rho;
+    double feq[27];     // InflowBoundary: compute_feq(rho, v), precomputed on the host
+};
+
+struct Layout {
+    int xl, yl, zl;     // local interior lengths (zl = planes owned by this slab)
+    int P;              // row pitch (elements)
+    int plane;          // P * (yl+2)
+    long long qstride;  // elements between consecutive q arrays
+};
+
+LBM_HD inline int cell_at(const Layout& g, int x, int y, int z)
+{
+    return z * g.plane + y * g.P + x + X_SHIFT;
+}
+
+struct SweepParams {
+    const double* __restrict__ src;   // collide field of the previous step
+    double* __restrict__ dst;         // becomes the collide field
+    const uint32_t* __restrict__ mask;
+    const uint8_t* __restrict__ kind;
+    const uint16_t* __restrict__ bcid;
+    const BcRec* __restrict__ bc;
+    Layout g;
+    int z0;            // first plane swept by this launch
+    int bx_shift;      // log2(threads along x per block)
+    int first;         // 1: boundary cells still hold host-visible values -> pull stored
+    int wrap_z;        // periodic z is closed inside this slab
+    double tau;
+    double omega;      // 1/tau (fast mode)
+    // optional remote copies of the slab-edge populations (peer ghost planes)
+    double* up_dst;    // receives c_z=+1 populations of plane z = zl
+    double* dn_dst;    // receives c_z=-1 populations of plane z = 1
+    long long up_qstride, dn_qstride;
+    long long up_off, dn_off;   // element offset of the target ghost plane
+};
+
+// ---------------------------------------------------------------------------
+// small runtime tables (slow paths only)
+template <int Q>
+struct Tables {
+    signed char c[27][3];
+    signed char q_of_cube[27];
+    double w[27];
+};
+template <int Q>
+constexpr Tables<Q> make_tables()
+{
+    Tables<Q> t{};
+    for (int i = 0; i < 27; ++i) t.q_of_cube[i] = -1;
+    for (int q = 0; q < Q; ++q) {
+        t.c[q][0] = (signed char) Lattice<Q>::cx(q);
+        t.c[q][1] = (signed char) Lattice<Q>::cy(q);
+        t.c[q][2] = (signed char) Lattice<Q>::cz(q);
+        t.q_of_cube[Lattice<Q>::cube(q)] = (signed char) q;
+        t.w[q] = Lattice<Q>::w(q);
+    }
+    return t;
+}
+__constant__ Tables<15> g_tab15 = make_tables<15>();
+__constant__ Tables<19> g_tab19 = make_tables<19>();
+__constant__ Tables<27> g_tab27 = make_tables<27>();
+template <int Q> __device__ __forceinline__ const Tables<Q>& tables();
+template <> __device__ __forceinline__ const Tables<15>& tables<15>() { return g_tab15; }
+template <> __device__ __forceinline__ const Tables<19>& tables<19>() { return g_tab19; }
+template <> __device__ __forceinline__ const Tables<27>& tables<27>() { return g_tab27; }
+
+// ---------------------------------------------------------------------------
+// arithmetic.  EXACT: IEEE add/mul/div in the reference's association, never
+// contracted (the __d*_rn intrinsics are not fused by nvcc).
+template <bool EXACT> struct Ar;
+template <> struct Ar<true> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+// collision.hpp:34-51, one entry; uu_term = u_dot_u / (2*C_S*C_S) is the same
+// value for every q in the reference and is hoisted by the callers.
+template <int Q, int q>
+__device__ __forceinline__ double feq_exact(double rho, double ux, double uy, double uz, double uu_term)
+{
+    using L = Lattice<Q>;
+    using A = Ar<true>;
+    constexpr double cx = L::cx(q), cy = L::cy(q), cz = L::cz(q);
+    double cu = A::add(0.0, A::mul(cx, ux));
+    cu = A::add(cu, A::mul(cy, uy));
+    cu = A::add(cu, A::mul(cz, uz));
+    double t = A::add(1.0, A::div(cu, CS2));
+    t = A::add(t, A::div(A::mul(cu, cu), TWO_CS4));
+    t = A::sub(t, uu_term);
+    return A::mul(A::mul(L::w(q), rho), t);
+}
+__device__ __forceinline__ double uu_term_exact(double ux, double uy, double uz)
+{
+    using A = Ar<true>;
+    double uu = A::add(0.0, A::mul(ux, ux));
+    uu = A::add(uu, A::mul(uy, uy));
+    uu = A::add(uu, A::mul(uz, uz));
+    return A::div(uu, TWO_CS2);
+}
+
+// moments of a register-resident cell: collision.hpp:7-31
+template <int Q>
+__device__ __forceinline__ void moments_exact(const double (&f)[Q], double& rho, double& mx, double& my, double& mz)
+{
+    using L = Lattice<Q>;
+    using A = Ar<true>;
+    rho = 0.0; mx = 0.0; my = 0.0; mz = 0.0;
+    static_for<Q>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        rho = A::add(rho, f[q]);
+        mx = A::add(mx, A::mul(f[q], (double) L::cx(q)));
+        my = A::add(my, A::mul(f[q], (double) L::cy(q)));
+        mz = A::add(mz, A::mul(f[q], (double) L::cz(q)));
+    });
+}
+
+template <int Q, bool EXACT>
+__device__ __forceinline__ void bgk_collide(double (&f)[Q], double tau, double omega)
+{
+    using L = Lattice<Q>;
+    if constexpr (EXACT) {
+        using A = Ar<true>;
+        double rho, mx, my, mz;
+        moments_exact<Q>(f, rho, mx, my, mz);
+        const double ux = A::div(mx, rho), uy = A::div(my, rho), uz = A::div(mz, rho);
+        const double uut = uu_term_exact(ux, uy, uz);
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            const double e = feq_exact<Q, q>(rho, ux, uy, uz, uut);
+            f[q] = A::sub(f[q], A::div(A::sub(f[q], e), tau));      // collision.hpp:68
+        });
+    } else {
+        // same formula, reciprocals and free contraction; opposite directions
+        // share the even part of the equilibrium
+        constexpr double I_CS2 = 1.0 / CS2, I_2CS4 = 1.0 / TWO_CS4, I_2CS2 = 1.0 / TWO_CS2;
+        double rho = 0.0, mx = 0.0, my = 0.0, mz = 0.0;
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            rho += f[q];
+            if constexpr (L::cx(q) == 1) mx += f[q];
+            if constexpr (L::cx(q) == -1) mx -= f[q];
+            if constexpr (L::cy(q) == 1) my += f[q];
+            if constexpr (L::cy(q) == -1) my -= f[q];
+            if constexpr (L::cz(q) == 1) mz += f[q];
+            if constexpr (L::cz(q) == -1) mz -= f[q];
+        });
+        const double ir = 1.0 / rho;
+        const double ux = mx * ir, uy = my * ir, uz = mz * ir;
+        const double base = 1.0 - (ux * ux + uy * uy + uz * uz) * I_2CS2;
+        static_for<(Q + 1) / 2>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            constexpr int qi = L::inv(q);
+            const double wr = L::w(q) * rho;
+            if constexpr (q == qi) {             // rest population
+                f[q] -= (f[q] - wr * base) * omega;
+            } else {
+                const double cu = (double) L::cx(q) * ux + (double) L::cy(q) * uy + (double) L::cz(q) * uz;
+                const double even = wr * (base + cu * cu * I_2CS4);
+                const double odd = wr * (cu * I_CS2);
+                f[q] -= (f[q] - (even + odd)) * omega;
+                f[qi] -= (f[qi] - (even - odd)) * omega;
+            }
+        });
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Link-wise boundary values.  The entry q of boundary cell
+// B = X - c_q is only ever read by the fluid cell X, and the reference computes
+// it from X's post-collision state of the previous step (boundary.hpp:26-28),
+// i.e. from  src[.][X].
+struct OwnMoments {
+    double rho, mx, my, mz;
+    bool have;
+};
+
+// sequential moments of the cell at index i of `src` (collision.hpp:7-31)
+template <int Q>
+__device__ __noinline__ void load_moments(const double* __restrict__ src, long long qstride, int i, OwnMoments* m)
+{
+    const Tables<Q>& T = tables<Q>();
+    double rho = 0.0, mx = 0.0, my = 0.0, mz = 0.0;
+    #pragma unroll 1
+    for (int q = 0; q < Q; ++q) {
+        const double v = src[q * qstride + i];
+        rho = __dadd_rn(rho, v);
+        mx = __dadd_rn(mx, __dmul_rn(v, (double) T.c[q][0]));
+        my = __dadd_rn(my, __dmul_rn(v, (double) T.c[q][1]));
+        mz = __dadd_rn(mz, __dmul_rn(v, (double) T.c[q][2]));
+    }
+    m->rho = rho; m->mx = mx; m->my = my; m->mz = mz; m->have = true;
+}
+
+// FreeSlipBoundary::collide, boundary.hpp:98-112, for the link (B, q), B = X - c_q.
+// Returns the value the reference leaves in B[q]; if no branch fires the stored
+// value stays.
+template <int Q>
+__device__ __noinline__ double freeslip_value(const double* __restrict__ src, const uint8_t* __restrict__ kind,
+                                              const Layout g, int iX, int q)
+{
+    const Tables<Q>& T = tables<Q>();
+    const int dx = T.c[q][0], dy = T.c[q][1], dz = T.c[q][2];
+    const int b = iX - (dz * g.plane + dy * g.P + dx);
+    auto at = [&](int ox, int oy, int oz) { return b + oz * g.plane + oy * g.P + ox; };
+    auto pick = [&](int cell, int u, int v, int w) {
+        const int qq = T.q_of_cube[(w + 1) * 9 + (v + 1) * 3 + (u + 1)];
+        return src[qq * g.qstride + cell];
+    };
+    int c;
+    if (kind[c = at(dx, 0, 0)] == K_FLUID) return pick(c, -dx, dy, dz);
+    if (kind[c = at(0, dy, 0)] == K_FLUID) return pick(c, dx, -dy, dz);
+    if (kind[c = at(0, 0, dz)] == K_FLUID) return pick(c, dx, dy, -dz);
+    if (kind[c = at(0, dy, dz)] == K_FLUID) return pick(c, dx, -dy, -dz);
+    if (kind[c = at(dx, 0, dz)] == K_FLUID) return pick(c, -dx, dy, -dz);
+    if (kind[c = at(dx, dy, 0)] == K_FLUID) return pick(c, -dx, -dy, dz);
+    return src[q * g.qstride + b];
+}
+
+// value of B[q] for handler (k, rec), computed from fluid cell X (index iX) in `src`
+template <int Q, bool EXACT, int q>
+__device__ __forceinline__ double link_value(const double* __restrict__ src, const uint8_t* __restrict__ kind,
+                                             const Layout& g, int iX, int k, const BcRec* __restrict__ rec,
+                                             OwnMoments& om)
+{
+    using L = Lattice<Q>;
+    constexpr int qi = L::inv(q);
+    constexpr int off = 0;
+    (void) off;
+    switch (k) {
+    case K_NOSLIP:                                            // boundary.hpp:28
+        return src[qi * g.qstride + iX];
+    case K_MOVINGWALL: {                                      // boundary.hpp:57-65
+        if (!om.have) load_moments<Q>(src, g.qstride, iX, &om);
+        const double finv = src[qi * g.qstride + iX];
+        constexpr double cx = L::cx(q), cy = L::cy(q), cz = L::cz(q);
+        // c_dot_u = ((0 + c0*u0) + c1*u1) + c2*u2 ;  finv + (((2.0*w)*rho)*cu)/(C_S*C_S)
+        double cu = __dadd_rn(0.0, __dmul_rn(cx, rec->v[0]));
+        cu = __dadd_rn(cu, __dmul_rn(cy, rec->v[1]));
+        cu = __dadd_rn(cu, __dmul_rn(cz, rec->v[2]));
+        constexpr double two_w = 2.0 * L::w(q);
+        if constexpr (EXACT) {
+            return __dadd_rn(finv, __ddiv_rn(__dmul_rn(__dmul_rn(two_w, om.rho), cu), CS2));
+        } else {
+            return finv + two_w * om.rho * cu * (1.0 / CS2);
+        }
+    }
+    case K_INFLOW:                                            // boundary.hpp:178
+        return rec->feq[q];
+    case K_OUTFLOW:                                           // boundary.hpp:143-147
+    case K_PRESSURE: {                                        // boundary.hpp:208-211
+        if (!om.have) load_moments<Q>(src, g.qstride, iX, &om);
+        const double r = rec->rho;                            // momentum / REFERENCE density
+        const double ux = __ddiv_rn(om.mx, r), uy = __ddiv_rn(om.my, r), uz = __ddiv_rn(om.mz, r);
+        const double uut = uu_term_exact(ux, uy, uz);
+        const double e = feq_exact<Q, q>(r, ux, uy, uz, uut);
+        const double ei = feq_exact<Q, qi>(r, ux, uy, uz, uut);
+        return __dsub_rn(__dadd_rn(e, ei), src[qi * g.qstride + iX]);
+    }
+    case K_FREESLIP:
+        return freeslip_value<Q>(src, kind, g, iX, q);
+    default: {                                                // NULL / PARALLEL: stored value
+        constexpr int o = 0;
+        (void) o;
+        return src[q * g.qstride + iX - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q))];
+    }
+    }
+}
+
+__device__ __forceinline__ int wrap1(int v, int l) { return v < 1 ? v + l : (v > l ? v - l : v); }
+
+// ---------------------------------------------------------------------------
+// K1: one thread per interior cell.  Bulk cells (mask == 0): Q coalesced loads,
+// BGK in registers, Q coalesced 128B-aligned stores -> 2*Q*8 bytes per update.
+template <int Q, bool EXACT>
+__global__ void __launch_bounds__(128) sweep_kernel(const SweepParams p)
+{
+    using L = Lattice<Q>;
+    const Layout& g = p.g;
+    const int bx = 1 << p.bx_shift;
+    const int x = 1 + blockIdx.x * bx + (threadIdx.x & (bx - 1));
+    const int y = 1 + blockIdx.y * (128 >> p.bx_shift) + (threadIdx.x >> p.bx_shift);
+    const int z = p.z0 + blockIdx.z;
+    if (x > g.xl || y > g.yl) return;
+    const int i = cell_at(g, x, y, z);
+    const uint32_t m = p.mask[i];
+    if (m & MASK_SKIP) return;
+
+    double f[Q];
+    if (m == 0) {
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            const int s = i - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
+            f[q] = p.src[q * g.qstride + s];
+        });
+    } else {
+        OwnMoments om;
+        om.have = false;
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            const int s = i - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
+            if (m & (1u << q)) {
+                const int k = p.kind[s];
+                if (k == K_PERIODIC) {
+                    const int sx = wrap1(x - L::cx(q), g.xl), sy = wrap1(y - L::cy(q), g.yl);
+                    const int sz = p.wrap_z ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
+                    f[q] = p.src[q * g.qstride + cell_at(g, sx, sy, sz)];
+                } else if (p.first) {
+                    f[q] = p.src[q * g.qstride + s];           // first step: stored values
+                } else {
+                    f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, p.bc + p.bcid[s], om);
+                }
+            } else {
+                f[q] = p.src[q * g.qstride + s];
+            }
+        });
+    }
+
+    bgk_collide<Q, EXACT>(f, p.tau, p.omega);
+
+    static_for<Q>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        p.dst[q * g.qstride + i] = f[q];
+    });
+    // slab edges: hand the populations that leave the slab to the neighbour
+    if (p.up_dst != nullptr && z == g.zl) {
+        const int ip = i - z * g.plane;
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            if constexpr (L::cz(q) == 1) p.up_dst[q * p.up_qstride + p.up_off + ip] = f[q];
+        });
+    }
+    if (p.dn_dst != nullptr && z == 1) {
+        const int ip = i - z * g.plane;
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            if constexpr (L::cz(q) == -1) p.dn_dst[q * p.dn_qstride + p.dn_off + ip] = f[q];
+        });
+    }
+}
+
+// K1g: ghost-shell cells that kept the fluid handler are BGK-collided in place in
+// the field that has just become the collide field (domain.hpp:147-155); they are
+// never streamed into (domain.hpp:121-123).
+template <int Q, bool EXACT>
+__global__ void ghost_fluid_kernel(double* __restrict__ field, long long qstride, const int* __restrict__ cells,
+                                   int n, double tau, double omega)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int i = cells[t];
+    double f[Q];
+    static_for<Q>([&](auto I) { constexpr int q = decltype(I)::value; f[q] = field[q * qstride + i]; });
+    bgk_collide<Q, EXACT>(f, tau, omega);
+    static_for<Q>([&](auto I) { constexpr int q = decltype(I)::value; field[q * qstride + i] = f[q]; });
+}
+
+// K2: the reference's non-fluid pass (domain.hpp:157-165) on the current collide
+// field, so that boundary cells read back through Domain::cell()/VTK hold what
+// the reference holds.  Reads fluid cells, writes non-fluid cells: no hazard.
+template <int Q, bool EXACT>
+__global__ void materialize_kernel(double* __restrict__ field, const uint8_t* __restrict__ kind,
+                                   const uint16_t* __restrict__ bcid, const BcRec* __restrict__ bc, const Layout g)
+{
+    using L = Lattice<Q>;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int z = blockIdx.z;
+    if (x > g.xl + 1) return;
+    const int b = cell_at(g, x, y, z);
+    const int k = kind[b];
+    if (k < K_NOSLIP || k > K_PRESSURE) return;
+    const BcRec* rec = bc + bcid[b];
+    static_for<Q>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        const int nx = x + L::cx(q), ny = y + L::cy(q), nz = z + L::cz(q);
+        const bool inb = nx > 0 && nx < g.xl + 1 && ny > 0 && ny < g.yl + 1 && nz > 0 && nz < g.zl + 1;
+        if (inb) {
+            const int n = b + (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
+            if (kind[n] == K_FLUID) {
+                OwnMoments om;
+                om.have = false;
+                field[q * g.qstride + b] = link_value<Q, EXACT, q>(field, kind, g, n, k, rec, om);
+            }
+        }
+    });
+}
+
+// K3: io/vtk.hpp:62-73 -> compute_density / compute_velocity (collision.hpp:7-31),
+// always in the reference's association.  Dense outputs in z,y,x order.
+template <int Q>
+__global__ void macroscopic_kernel(const double* __restrict__ field, const Layout g,
+                                   double* __restrict__ rho_out, double* __restrict__ u_out)
+{
+    const int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = 1 + blockIdx.y;
+    const int z = 1 + blockIdx.z;
+    if (x > g.xl) return;
+    const int i = cell_at(g, x, y, z);
+    double f[Q];
+    static_for<Q>([&](auto I) { constexpr int q = decltype(I)::value; f[q] = field[q * g.qstride + i]; });
+    double rho, mx, my, mz;
+    moments_exact<Q>(f, rho, mx, my, mz);
+    const long long o = ((long long) (z - 1) * g.yl + (y - 1)) * g.xl + (x - 1);
+    if (rho_out) rho_out[o] = rho;
+    if (u_out) {
+        u_out[3 * o + 0] = __ddiv_rn(mx, rho);
+        u_out[3 * o + 1] = __ddiv_rn(my, rho);
+        u_out[3 * o + 2] = __ddiv_rn(mz, rho);
+    }
+}
+
+// per-block partial sums over interior fluid cells: mass, sum |u|^2, max |u|^2
+template <int Q>
+__global__ void diagnostics_kernel(const double* __restrict__ field, const uint8_t* __restrict__ kind, const Layout g,
+                                   double* __restrict__ partial /* [nblocks][3] */)
+{
+    __shared__ double sh[3][128];
+    const int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = 1 + blockIdx.y;
+    const int z = 1 + blockIdx.z;
+    double mass = 0.0, ke = 0.0, um = 0.0;
+    if (x <= g.xl) {
+        const int i = cell_at(g, x, y, z);
+        if (kind[i] == K_FLUID) {
+            double f[Q];
+            static_for<Q>([&](auto I) { constexpr int q = decltype(I)::value; f[q] = field[q * g.qstride + i]; });
+            double rho, mx, my, mz;
+            moments_exact<Q>(f, rho, mx, my, mz);
+            const double ux = mx / rho, uy = my / rho, uz = mz / rho;
+            mass = rho;
+            ke = ux * ux + uy * uy + uz * uz;
+            um = ke;
+        }
+    }
+    sh[0][threadIdx.x] = mass; sh[1][threadIdx.x] = ke; sh[2][threadIdx.x] = um;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int) threadIdx.x < s) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+            sh[2][threadIdx.x] = fmax(sh[2][threadIdx.x], sh[2][threadIdx.x + s]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const long long blk = ((long long) blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        partial[3 * blk + 0] = sh[0][0];
+        partial[3 * blk + 1] = sh[1][0];
+        partial[3 * blk + 2] = sh[2][0];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K5: set-up kernels
+
+// Cell ctor, cell.hpp:9-15: pdf = weights (padding included, harmless)
+template <int Q>
+__global__ void fill_weights_kernel(double* __restrict__ field, long long qstride)
+{
+    const Tables<Q>& T = tables<Q>();
+    const long long n = qstride * Q;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x)
+        field[i] = T.w[i / qstride];
+}
+
+// link mask: bit q set <=> the pull source X - c_q of interior fluid cell X is not fluid
+template <int Q>
+__global__ void build_mask_kernel(const uint8_t* __restrict__ kind, uint32_t* __restrict__ mask, const Layout g)
+{
+    const Tables<Q>& T = tables<Q>();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int z = blockIdx.z;
+    if (x > g.xl + 1) return;
+    const int i = cell_at(g, x, y, z);
+    const bool interior = x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1;
+    uint32_t m = 0;
+    if (!interior || kind[i] != K_FLUID) {
+        m = MASK_SKIP;
+    } else {
+        for (int q = 0; q < Q; ++q) {
+            const int s = i - (T.c[q][2] * g.plane + T.c[q][1] * g.P + T.c[q][0]);
+            if (kind[s] != K_FLUID) m |= 1u << q;
+        }
+    }
+    mask[i] = m;
+}
+
+// dense (reference idx order) byte/short maps -> padded device maps, planes [z0, z0+nz)
+template <typename T>
+__global__ void scatter_map_kernel(const T* __restrict__ dense, T* __restrict__ padded, const Layout g, int z0)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int zz = blockIdx.z;
+    if (x > g.xl + 1) return;
+    padded[cell_at(g, x, y, z0 + zz)] = dense[((long long) zz * (g.yl + 2) + y) * (g.xl + 2) + x];
+}
+
+// AoS chunk (reference Cell order, planes [z0, z0+nz)) <-> padded SoA
+template <int Q, bool TO_DEVICE_LAYOUT>
+__global__ void transpose_aos_kernel(double* __restrict__ aos, double* __restrict__ field, const Layout g, int z0)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int zz = blockIdx.z;
+    if (x > g.xl + 1) return;
+    const int i = cell_at(g, x, y, z0 + zz);
+    double* a = aos + (((long long) zz * (g.yl + 2) + y) * (g.xl + 2) + x) * Q;
+    #pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        if (TO_DEVICE_LAYOUT) field[q * g.qstride + i] = a[q];
+        else a[q] = field[q * g.qstride + i];
+    }
+}
+
+// f = feq(rho,u) with compute_feq's association (collision.hpp:34-51), planes [z0,z0+nz)
+template <int Q>
+__global__ void equilibrium_kernel(const double* __restrict__ rho, const double* __restrict__ u,
+                                   double* __restrict__ field, const Layout g, int z0)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int zz = blockIdx.z;
+    if (x > g.xl + 1) return;
+    const int i = cell_at(g, x, y, z0 + zz);
+    const long long d = ((long long) zz * (g.yl + 2) + y) * (g.xl + 2) + x;
+    const double r = rho[d], ux = u[3 * d], uy = u[3 * d + 1], uz = u[3 * d + 2];
+    const double uut = uu_term_exact(ux, uy, uz);
+    static_for<Q>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        field[q * g.qstride + i] = feq_exact<Q, q>(r, ux, uy, uz, uut);
+    });
+}
+
+// copy one x-y plane of selected populations (halo unpack / pack)
+__global__ void copy_planes_kernel(const double* __restrict__ src, double* __restrict__ dst, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+} // namespace lbmb200

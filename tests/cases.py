@@ -1,0 +1,95 @@
+"""Scenario builders shared by the CPU and GPU tests (inputs fed to BOTH the
+oracle and the CUDA path).  Box lists use the format of tests/_oracle.py."""
+import numpy as np
+
+import _oracle as O
+
+
+def cavity(n, lid=(0.05, 0.0, 0.0)):
+    return dict(xl=n, yl=n, zl=n, boxes=O.cavity_boxes(n, n, n, lid))
+
+
+def channel(xl, yl, zl, block=None, u_in=(0.03, 0.0, 0.0)):
+    b = O.channel_boxes(xl, yl, zl, u_in)
+    if block is not None:
+        b.insert(2, (O.NOSLIP, (0.0, 0.0, 0.0), 1.0, tuple(block)))
+    return dict(xl=xl, yl=yl, zl=zl, boxes=b)
+
+
+def shearflow():
+    """build/scenarios/shearflow.xml"""
+    return dict(xl=8, yl=8, zl=20, boxes=O.face_boxes(8, 8, 20, [
+        ("z0", O.PRESSURE, None, 1.005), ("zmax", O.OUTFLOW), ("x0", O.FREESLIP), ("xmax", O.FREESLIP),
+        ("y0", O.NOSLIP), ("ymax", O.NOSLIP)]))
+
+
+def step_flow():
+    """build/scenarios/step.xml"""
+    return dict(xl=30, yl=30, zl=50, boxes=O.face_boxes(30, 30, 50, [
+        ((17, 31, 0, 31, 0, 0), O.INFLOW, (0.0, 0.0, 0.05)), ((0, 16, 0, 31, 0, 25), O.NOSLIP),
+        ("zmax", O.OUTFLOW), ("y0", O.NOSLIP), ("ymax", O.NOSLIP), ("x0", O.NOSLIP), ("xmax", O.NOSLIP)]))
+
+
+def masked_pipe(xl=24, yl=10, zl=10):
+    zz, yy, xx = np.meshgrid(np.arange(zl), np.arange(yl), np.arange(xl), indexing="ij")
+    mask = (((yy - (yl - 1) / 2) ** 2 + (zz - (zl - 1) / 2) ** 2) < (min(yl, zl) / 2 - 1) ** 2).astype(np.uint8)
+    return dict(xl=xl, yl=yl, zl=zl, boxes=O.channel_boxes(xl, yl, zl), fluid_mask=mask)
+
+
+def weird(Q, seed=0):
+    """uncovered ghost shell, ParallelBoundary face, interior free-slip block, oblique lid, random state"""
+    xl, yl, zl = 10, 9, 8
+    rng = np.random.default_rng(seed)
+    boxes = O.face_boxes(xl, yl, zl, [("z0", O.NOSLIP), ("x0", O.PARALLEL), ((4, 6, 3, 5, 2, 4), O.FREESLIP),
+                                      ("ymax", O.MOVINGWALL, (0.01, 0.02, -0.03))])
+    f0 = rng.random(((xl + 2) * (yl + 2) * (zl + 2), Q)) * 0.1 + 0.05
+    return dict(xl=xl, yl=yl, zl=zl, boxes=boxes, f_init=f0)
+
+
+def periodic_random(Q, n=8, seed=1):
+    rng = np.random.default_rng(seed)
+    f0 = rng.random(((n + 2) ** 3, Q)) * 0.1 + 0.05
+    return dict(xl=n, yl=n, zl=n, boxes=[], f_init=f0, periodic=True)
+
+
+def periodic_shell_boxes(xl, yl, zl):
+    """the PERIODIC extension of the CUDA path: every ghost-shell cell mirrors its wrapped image"""
+    return O.face_boxes(xl, yl, zl, [(e, O.PERIODIC) for e in ("z0", "zmax", "x0", "xmax", "y0", "ymax")])
+
+
+def interior_index(xl, yl, zl):
+    """flat Domain::idx of the interior cells in z,y,x order"""
+    z, y, x = np.meshgrid(np.arange(1, zl + 1), np.arange(1, yl + 1), np.arange(1, xl + 1), indexing="ij")
+    return (x + (xl + 2) * y + (xl + 2) * (yl + 2) * z).reshape(-1)
+
+
+def taylor_green(n, Q, U0=0.01, mode="xy"):
+    """rho,u on all (n+2)^3 cells (cell centres at i-1/2)."""
+    cs2 = 0.57735026919 ** 2
+    k = 2 * np.pi / n
+    idx = np.arange(n + 2) - 0.5
+    Z, Y, X = np.meshgrid(idx, idx, idx, indexing="ij")
+    u = np.zeros((n + 2, n + 2, n + 2, 3))
+    if mode == "3d":
+        u[..., 0] = U0 * np.sin(k * X) * np.cos(k * Y) * np.cos(k * Z)
+        u[..., 1] = -U0 * np.cos(k * X) * np.sin(k * Y) * np.cos(k * Z)
+        rho = 1 + U0 ** 2 / (16 * cs2) * (np.cos(2 * k * X) + np.cos(2 * k * Y)) * (np.cos(2 * k * Z) + 2)
+    elif mode == "diag":
+        # 2-D vortex in the plane spanned by (1,1,0)/sqrt2 and z, wave number k along each
+        A = (X + Y)
+        a, b = k * A, k * Z * 2
+        ka, kb = k * np.sqrt(2.0), 2 * k
+        # stream function psi = cos(a) cos(b): u_A = -dpsi/dZ, u_Z = dpsi/dA
+        uA = U0 * np.cos(a) * np.sin(b)
+        uZ = -U0 * (ka / kb) * np.sin(a) * np.cos(b)
+        u[..., 0] = uA / np.sqrt(2.0)
+        u[..., 1] = uA / np.sqrt(2.0)
+        u[..., 2] = uZ
+        rho = np.ones_like(X)
+    else:
+        a_ax, b_ax = {"xy": (X, Y), "yz": (Y, Z), "xz": (X, Z)}[mode]
+        ia, ib = {"xy": (0, 1), "yz": (1, 2), "xz": (0, 2)}[mode]
+        u[..., ia] = U0 * np.sin(k * a_ax) * np.cos(k * b_ax)
+        u[..., ib] = -U0 * np.cos(k * a_ax) * np.sin(k * b_ax)
+        rho = 1 - U0 ** 2 / (4 * cs2) * (np.cos(2 * k * a_ax) + np.cos(2 * k * b_ax))
+    return rho, u

@@ -1,0 +1,146 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the
+same inputs.  EXACT arithmetic must be bit-identical; FAST arithmetic must stay
+within the north star's fp64 gate (max relative error 1e-12)."""
+import numpy as np
+import pytest
+
+import _oracle as O
+import cases
+
+pytestmark = pytest.mark.gpu
+
+TAU = 0.6
+REL_TOL = 1e-12      # BASELINE.json north_star: "max relative error <= 1e-12"
+
+
+def checker():
+    return O.ref() or O.oracle()
+
+
+def run_gpu(Q, case, steps, exact, periodic_kind=False):
+    from lbm_b200 import capi
+    xl, yl, zl = case["xl"], case["yl"], case["zl"]
+    with capi.Domain(Q, xl, yl, zl, TAU, exact=exact) as d:
+        if case.get("fluid_mask") is not None:
+            d.set_fluid_mask(case["fluid_mask"])
+        boxes = list(case["boxes"])
+        if periodic_kind:
+            boxes = cases.periodic_shell_boxes(xl, yl, zl)
+        if boxes:
+            d.set_boxes(boxes)
+        if case.get("f_init") is not None:
+            d.upload(case["f_init"])
+        d.step(steps)
+        f = d.download()
+        rho, u = d.macroscopic()
+        launches = d.launch_count()
+    assert launches >= steps
+    return dict(f=f, rho=rho, u=u)
+
+
+def run_cpu(Q, case, steps):
+    kw = {k: case[k] for k in ("f_init", "fluid_mask", "periodic") if k in case}
+    return checker().run(Q, case["xl"], case["yl"], case["zl"], TAU, case["boxes"], steps, **kw)
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def assert_bitwise(name, got, want, sel=None):
+    g, w = (got, want) if sel is None else (got[sel], want[sel])
+    # -0.0 == +0.0 is accepted; everything else must agree to the last bit
+    bad = (bits(g) != bits(w)) & ~((g == 0.0) & (w == 0.0))
+    assert not bad.any(), "%s: %d of %d values differ, first at %s: %r vs %r" % (
+        name, bad.sum(), bad.size, np.argwhere(bad)[0], g[bad][0], w[bad][0])
+
+
+def rel_err(got, want):
+    scale = np.maximum(np.abs(want), 1e-300)
+    return float(np.max(np.abs(got - want) / scale))
+
+
+CASES = {
+    "cavity16": (lambda Q: cases.cavity(16), 60),
+    "channel_block": (lambda Q: cases.channel(40, 12, 10, block=(10, 14, 4, 8, 0, 5)), 60),
+    "shearflow": (lambda Q: cases.shearflow(), 80),
+    "step": (lambda Q: cases.step_flow(), 40),
+    "masked_pipe": (lambda Q: cases.masked_pipe(), 40),
+    "weird": (lambda Q: cases.weird(Q), 25),
+    "one_step": (lambda Q: cases.cavity(6), 1),
+    "two_steps": (lambda Q: cases.channel(9, 5, 4), 2),
+}
+
+
+@pytest.mark.parametrize("Q", [15, 19, 27])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_exact_mode_is_bit_identical(Q, name):
+    make, steps = CASES[name]
+    case = make(Q)
+    cpu = run_cpu(Q, case, steps)
+    gpu = run_gpu(Q, case, steps, exact=True)
+    assert_bitwise(name + " populations", gpu["f"], cpu["f"])
+    assert_bitwise(name + " density", gpu["rho"], cpu["rho"])
+    assert_bitwise(name + " velocity", gpu["u"], cpu["u"])
+
+
+@pytest.mark.parametrize("Q", [15, 19, 27])
+@pytest.mark.parametrize("name", ["cavity16", "channel_block", "shearflow", "step", "masked_pipe", "weird"])
+def test_fast_mode_within_tolerance(Q, name):
+    make, steps = CASES[name]
+    case = make(Q)
+    cpu = run_cpu(Q, case, steps)
+    gpu = run_gpu(Q, case, steps, exact=False)
+    fluid = cpu["kind"] == O.FLUID
+    assert rel_err(gpu["f"][fluid], cpu["f"][fluid]) <= REL_TOL
+    assert rel_err(gpu["f"], cpu["f"]) <= REL_TOL
+    assert rel_err(gpu["rho"], cpu["rho"]) <= REL_TOL
+    umax = np.abs(cpu["u"]).max()
+    assert np.abs(gpu["u"] - cpu["u"]).max() <= REL_TOL * max(umax, 1e-30) * 10 or umax == 0
+
+
+@pytest.mark.parametrize("Q", [15, 19, 27])
+def test_periodic_extension_equals_ghost_copy_recipe(Q):
+    case = cases.periodic_random(Q)
+    steps = 30
+    cpu = run_cpu(Q, case, steps)
+    gpu = run_gpu(Q, case, steps, exact=True, periodic_kind=True)
+    inner = cases.interior_index(case["xl"], case["yl"], case["zl"])
+    assert_bitwise("periodic populations", gpu["f"], cpu["f"], inner)
+    assert_bitwise("periodic density", gpu["rho"], cpu["rho"])
+
+
+@pytest.mark.parametrize("Q", [19])
+def test_long_run_cavity64_fast(Q):
+    """config 1 of BASELINE.json: cavity D3Q19 64^3; 1000 steps like build/config.cfg"""
+    case = cases.cavity(64)
+    steps = 1000
+    cpu = run_cpu(Q, case, steps)
+    gpu = run_gpu(Q, case, steps, exact=False)
+    fluid = cpu["kind"] == O.FLUID
+    assert rel_err(gpu["f"][fluid], cpu["f"][fluid]) <= REL_TOL
+    assert rel_err(gpu["rho"], cpu["rho"]) <= REL_TOL
+    assert np.abs(gpu["u"] - cpu["u"]).max() <= REL_TOL * np.abs(cpu["u"]).max()
+
+
+def test_download_upload_roundtrip_and_restart():
+    """populations survive download -> upload, and a restarted run continues bit-exactly"""
+    from lbm_b200 import capi
+    Q, case = 19, cases.channel(20, 8, 6, block=(5, 8, 2, 5, 0, 3))
+    with capi.Domain(Q, case["xl"], case["yl"], case["zl"], TAU, exact=True) as a:
+        a.set_boxes(case["boxes"])
+        a.step(20)
+        mid = a.download()
+        soa = a.download(layout=capi.SOA)
+        assert np.array_equal(soa.T, mid)
+        a.step(15)
+        end = a.download()
+    with capi.Domain(Q, case["xl"], case["yl"], case["zl"], TAU, exact=True) as b:
+        b.set_boxes(case["boxes"])
+        b.upload(mid)
+        assert np.array_equal(b.download(), mid)
+        b.step(15)
+        end_b = b.download()
+    assert_bitwise("restart", end_b, end)
+    cpu = run_cpu(Q, case, 35)
+    assert_bitwise("restart vs oracle", end, cpu["f"])
