@@ -90,7 +90,9 @@ class SlabRunner:
         self.down, self.up = neighbours(rank, world, periodic_z)
         self.transport = transport if world > 1 else "none"
         self.group = group
-        self.stream = torch.cuda.current_stream()
+        # a dedicated non-default stream: the library's kernels, the NCCL ordering events and the
+        # timing events of bench.py all refer to it
+        self.stream = torch.cuda.Stream(device=device)
         self.dom.set_stream(self.stream.cuda_stream)
         if self.transport == "nccl":
             self._wrap_planes()
@@ -153,8 +155,9 @@ class SlabRunner:
             self.dom.step(n)
             return
         fn = self._step_nccl if self.transport == "nccl" else self._step_p2p
-        for _ in range(n):
-            fn()
+        with self.torch.cuda.stream(self.stream):
+            for _ in range(n):
+                fn()
 
     def close(self):
         self.dom.close()
