@@ -1,0 +1,411 @@
+// include/lbm/domain.h -- Domain<M>: the lattice, resident on one or more B200s.
+//
+// Public interface of the reference's include/domain.h:22-55 (constructor,
+// getters, idx/in_bounds/cell, setBoundaryCondition, set_nonfluid_cells_nullcollide,
+// stream/collide/swap, create_subdomain).  What changes underneath:
+//   * storage: the two Lattice_fields of domain.h:13-14 become device-resident
+//     padded structure-of-arrays buffers owned through the C ABI (lbm_b200.h);
+//   * stream(); swap(); collide();  (src/main.cpp:50-52) is ONE fused kernel launch,
+//     issued by collide() once the three calls have been made in that order;
+//   * the lattice is split into z-slabs over `lbm::device::gpus()` GPUs; the sweep
+//     stores the populations leaving a slab into the neighbour's ghost plane over
+//     NVLink (what parallel.h / create_subdomain only sketched);
+//   * Domain::cell() serves a host mirror that is downloaded on demand and uploaded
+//     before the next step if a mutable reference was handed out -- set-up,
+//     inspection and tests only, never inside the time loop.
+// Errors of the C ABI surface as std::runtime_error, so main's catch block
+// (src/main.cpp:68-71) behaves as before.
+#pragma once
+#include <cassert>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "lbmdefinitions.h"
+#include "collision.h"
+#include "parallel.h"
+#include "helper.h"
+
+namespace lbm
+{
+
+namespace device
+{
+// process-wide knobs the fixed Domain constructor signature has no room for
+inline int& gpus_ref()
+{
+    static int n = [] { const char* e = std::getenv("LBM_B200_GPUS"); return e ? std::max(1, std::atoi(e)) : 1; }();
+    return n;
+}
+inline int& arithmetic_ref()
+{
+    static int m = [] {
+        const char* e = std::getenv("LBM_B200_ARITHMETIC");
+        return (e && std::string(e) == "exact") ? LBM_B200_EXACT : LBM_B200_FAST;
+    }();
+    return m;
+}
+inline void set_gpus(int n) { gpus_ref() = n < 1 ? 1 : n; }
+inline int gpus() { return gpus_ref(); }
+inline void set_arithmetic(int mode) { arithmetic_ref() = mode; }
+inline int arithmetic() { return arithmetic_ref(); }
+
+inline void check(int rc, const char* what)
+{
+    if (rc != 0) throw std::runtime_error(std::string(what) + ": " + lbm_b200_last_error());
+}
+} // namespace device
+
+template <typename lattice_model>
+class Domain
+{
+    const FluidCollision<lattice_model>* const collision;
+    const std::size_t xl { 0 }, yl { 0 }, zl { 0 };
+    double xo, yo, zo;
+    double xs, ys, zs;
+
+    struct Slab {
+        lbm_b200_t* handle;
+        std::size_t z_first, zl_local;
+    };
+    std::vector<Slab> slabs;
+
+    // handler bookkeeping: id 0 is the fluid operator
+    std::vector<const Collision<lattice_model>*> handlers;
+    std::vector<std::uint16_t> handler_id;      // per cell, Domain::idx order
+    bool geometry_dirty { true };
+
+    // host mirror behind cell()
+    mutable Lattice_field<lattice_model> mirror;
+    mutable bool mirror_valid { false };
+    mutable bool mirror_dirty { false };
+
+    bool streamed { false }, swapped { false };
+    std::uint64_t steps_done { 0 };
+
+    std::size_t plane_cells() const { return (xl + 2) * (yl + 2); }
+    std::size_t all_cells() const { return plane_cells() * (zl + 2); }
+
+    std::uint16_t intern(const Collision<lattice_model>* h)
+    {
+        for (std::size_t i = 0; i < handlers.size(); ++i)
+            if (handlers[i] == h) return std::uint16_t(i);
+        if (h->device_kind() < 0)
+            throw std::logic_error("this collision operator only exists as host code (device_kind() < 0); "
+                    "user-defined operators cannot run in the CUDA sweep and there is no CPU fallback");
+        if (handlers.size() >= 65535) throw std::logic_error("more than 65535 distinct collision handlers");
+        handlers.push_back(h);
+        return std::uint16_t(handlers.size() - 1);
+    }
+
+    void push_geometry()
+    {
+        if (!geometry_dirty) return;
+        std::vector<lbm_b200_bc> table(handlers.size());
+        for (std::size_t i = 0; i < handlers.size(); ++i) table[i] = handlers[i]->descriptor();
+        std::vector<std::uint8_t> kind(all_cells());
+        for (std::size_t i = 0; i < kind.size(); ++i) kind[i] = std::uint8_t(table[handler_id[i]].kind);
+        for (auto& s : slabs) {
+            const std::size_t off = (s.z_first - 1) * plane_cells();   // local plane 0 == global plane z_first-1
+            device::check(lbm_b200_set_geometry(s.handle, kind.data() + off, handler_id.data() + off,
+                    table.data(), int(table.size())), "lbm_b200_set_geometry");
+        }
+        geometry_dirty = false;
+    }
+
+    // mirror <-> device
+    void pull_mirror() const
+    {
+        if (mirror_valid) return;
+        auto* self = const_cast<Domain*>(this);
+        self->push_geometry();
+        constexpr std::size_t Q = lattice_model::Q;
+        if (mirror.empty()) mirror.assign(all_cells(), Cell<lattice_model>(collision));
+        std::vector<double> buf;
+        for (std::size_t si = 0; si < slabs.size(); ++si) {
+            const auto& s = slabs[si];
+            const std::size_t local = plane_cells() * (s.zl_local + 2);
+            buf.resize(local * Q);
+            device::check(lbm_b200_download_populations(s.handle, buf.data(), LBM_B200_AOS, LBM_B200_COLLIDE_FIELD),
+                    "lbm_b200_download_populations");
+            // own planes, plus the physical ghost planes at the two ends of the stack
+            const std::size_t p0 = si == 0 ? 0 : 1;
+            const std::size_t p1 = si + 1 == slabs.size() ? s.zl_local + 1 : s.zl_local;
+            for (std::size_t p = p0; p <= p1; ++p)
+                for (std::size_t c = 0; c < plane_cells(); ++c) {
+                    Cell<lattice_model>& dst = mirror[(s.z_first - 1 + p) * plane_cells() + c];
+                    std::memcpy(dst.data(), buf.data() + (p * plane_cells() + c) * Q, Q * sizeof(double));
+                }
+        }
+        for (std::size_t i = 0; i < mirror.size(); ++i) mirror[i].set_collision_handler(handlers[handler_id[i]]);
+        mirror_valid = true;
+        mirror_dirty = false;
+    }
+
+    void push_mirror()
+    {
+        if (!mirror_dirty) return;
+        constexpr std::size_t Q = lattice_model::Q;
+        // handlers may have been changed through Cell::set_collision_handler
+        for (std::size_t i = 0; i < mirror.size(); ++i) {
+            const auto* h = mirror[i].get_collision_handler();
+            if (h != handlers[handler_id[i]]) {
+                handler_id[i] = intern(h);
+                geometry_dirty = true;
+            }
+        }
+        std::vector<double> buf;
+        for (auto& s : slabs) {
+            const std::size_t local = plane_cells() * (s.zl_local + 2);
+            buf.resize(local * Q);
+            const std::size_t off = (s.z_first - 1) * plane_cells();
+            for (std::size_t c = 0; c < local; ++c) std::memcpy(buf.data() + c * Q, mirror[off + c].data(), Q * sizeof(double));
+            device::check(lbm_b200_upload_populations(s.handle, buf.data(), LBM_B200_AOS, LBM_B200_COLLIDE_FIELD),
+                    "lbm_b200_upload_populations");
+        }
+        mirror_dirty = false;
+    }
+
+    void require_idle(const char* what) const
+    {
+        if (streamed || swapped)
+            throw std::logic_error(std::string(what) + " between stream() and collide(): the three calls "
+                    "stream(); swap(); collide(); execute as one fused device step");
+    }
+
+public:
+    Domain(std::size_t xl, std::size_t yl, std::size_t zl, FluidCollision<lattice_model>& _collision,
+            double xorigin = 0, double yorigin = 0, double zorigin = 0,
+            double xspacing = 1, double yspacing = 1, double zspacing = 1)
+        : collision { &_collision }, xl { xl }, yl { yl }, zl { zl },
+          xo { xorigin }, yo { yorigin }, zo { zorigin }, xs { xspacing }, ys { yspacing }, zs { zspacing }
+    {
+        const auto* bgk = dynamic_cast<const BGKCollision<lattice_model>*>(collision);
+        if (!bgk)
+            throw std::logic_error("Domain: only BGKCollision can run in the CUDA sweep (the reference asserts "
+                    "collision-model == bgk as well, io/configuration.h:126-128)");
+        handlers.push_back(collision);
+        handler_id.assign(all_cells(), 0);
+        int n = device::gpus();
+        if (std::size_t(n) > zl) n = int(zl);
+        const int visible = lbm_b200_device_count();
+        if (visible < 1) throw std::runtime_error("Domain: no CUDA device visible; there is no CPU fallback");
+        if (n > visible) throw std::runtime_error("Domain: " + std::to_string(n) + " GPUs requested, " + std::to_string(visible) + " visible");
+        std::size_t z = 1;
+        for (int r = 0; r < n; ++r) {
+            const std::size_t nz = zl / n + (std::size_t(r) < zl % n ? 1 : 0);
+            lbm_b200_t* h = nullptr;
+            const int rc = lbm_b200_create_slab(&h, int(lattice_model::Q), xl, yl, zl, z, nz, bgk->relaxation_time(), n > 1 ? r : -1);
+            if (rc != 0) {
+                const std::string msg = lbm_b200_last_error();
+                for (auto& s : slabs) lbm_b200_destroy(s.handle);
+                throw std::runtime_error("lbm_b200_create_slab: " + msg);
+            }
+            slabs.push_back({ h, z, nz });
+            device::check(lbm_b200_set_arithmetic(h, device::arithmetic()), "lbm_b200_set_arithmetic");
+            z += nz;
+        }
+        for (std::size_t r = 0; r + 1 < slabs.size(); ++r) {
+            device::check(lbm_b200_connect_local(slabs[r].handle, LBM_B200_UP, slabs[r + 1].handle), "lbm_b200_connect_local");
+            device::check(lbm_b200_connect_local(slabs[r + 1].handle, LBM_B200_DOWN, slabs[r].handle), "lbm_b200_connect_local");
+        }
+    }
+
+    ~Domain()
+    {
+        for (auto& s : slabs) lbm_b200_destroy(s.handle);
+    }
+    Domain(const Domain&) = delete;
+    Domain& operator=(const Domain&) = delete;
+
+    // Getters
+    auto xlength() const -> decltype(xl) { return xl; }
+    auto ylength() const -> decltype(yl) { return yl; }
+    auto zlength() const -> decltype(zl) { return zl; }
+    auto xorigin() const -> decltype(xo) { return xo; }
+    auto yorigin() const -> decltype(yo) { return yo; }
+    auto zorigin() const -> decltype(zo) { return zo; }
+    auto xspacing() const -> decltype(xs) { return xs; }
+    auto yspacing() const -> decltype(ys) { return ys; }
+    auto zspacing() const -> decltype(zs) { return zs; }
+
+    // Helper functions
+    auto idx(int x, int y, int z) const -> int { return x + int(xl + 2) * y + int((xl + 2) * (yl + 2)) * z; }
+    auto in_bounds(int x, int y, int z) const -> bool
+    {
+        return x > 0 && x < int(xl) + 1 && y > 0 && y < int(yl) + 1 && z > 0 && z < int(zl) + 1;
+    }
+    auto cell(int x, int y, int z) const -> const Cell<lattice_model>&
+    {
+        require_idle("Domain::cell()");
+        pull_mirror();
+        return mirror[idx(x, y, z)];
+    }
+    auto cell(int x, int y, int z) -> Cell<lattice_model>&
+    {
+        require_idle("Domain::cell()");
+        pull_mirror();
+        mirror_dirty = true;   // a mutable reference escapes: assume it is written
+        return mirror[idx(x, y, z)];
+    }
+
+    // handler of a cell without touching the population mirror
+    auto handler(int x, int y, int z) const -> const Collision<lattice_model>*
+    {
+        if (mirror_valid && mirror_dirty) return mirror[idx(x, y, z)].get_collision_handler();
+        return handlers[handler_id[idx(x, y, z)]];
+    }
+
+    // domain.hpp:101-113: interior non-fluid cells without any interior fluid neighbour get the
+    // do-nothing handler.  A pure optimisation in the reference; the device sweep never visits
+    // such cells anyway, so only the handler bookkeeping changes.
+    auto set_nonfluid_cells_nullcollide() -> void
+    {
+        require_idle("set_nonfluid_cells_nullcollide()");
+        if (mirror_valid && mirror_dirty) push_mirror();
+        static NullCollision<lattice_model> null_collision;
+        std::vector<std::size_t> lonely;
+        for (int z = 1; z < int(zl) + 1; ++z)
+            for (int y = 1; y < int(yl) + 1; ++y)
+                for (int x = 1; x < int(xl) + 1; ++x) {
+                    if (handlers[handler_id[idx(x, y, z)]]->is_fluid()) continue;
+                    bool vicinity = false;
+                    for (std::size_t q = 0; q < lattice_model::Q && !vicinity; ++q) {
+                        const int nx = x + int(lattice_model::velocities[q][0]);
+                        const int ny = y + int(lattice_model::velocities[q][1]);
+                        const int nz = z + int(lattice_model::velocities[q][2]);
+                        vicinity = in_bounds(nx, ny, nz) && handlers[handler_id[idx(nx, ny, nz)]]->is_fluid();
+                    }
+                    if (!vicinity) lonely.push_back(std::size_t(idx(x, y, z)));
+                }
+        if (lonely.empty()) return;
+        const std::uint16_t id = intern(&null_collision);
+        for (auto i : lonely) handler_id[i] = id;
+        if (mirror_valid)
+            for (auto i : lonely) mirror[i].set_collision_handler(&null_collision);
+        geometry_dirty = true;
+    }
+
+    // domain.hpp:175-194: inclusive box, later calls overwrite earlier ones
+    auto setBoundaryCondition(NonFluidCollision<lattice_model>& condition,
+            std::size_t x0, std::size_t xE, std::size_t y0, std::size_t yE, std::size_t z0, std::size_t zE) -> void
+    {
+        require_idle("setBoundaryCondition()");
+        if (!(xE >= x0 && yE >= y0 && zE >= z0) || !(xE < xl + 2 && yE < yl + 2 && zE < zl + 2))
+            throw std::out_of_range("setBoundaryCondition: extent outside the domain (the reference asserts this, domain.hpp:180-181)");
+        if (mirror_valid && mirror_dirty) push_mirror();
+        const std::uint16_t id = intern(&condition);
+        for (auto z = z0; z <= zE; ++z)
+            for (auto y = y0; y <= yE; ++y)
+                for (auto x = x0; x <= xE; ++x) handler_id[std::size_t(idx(int(x), int(y), int(z)))] = id;
+        if (mirror_valid)
+            for (auto z = z0; z <= zE; ++z)
+                for (auto y = y0; y <= yE; ++y)
+                    for (auto x = x0; x <= xE; ++x) mirror[std::size_t(idx(int(x), int(y), int(z)))].set_collision_handler(&condition);
+        geometry_dirty = true;
+    }
+
+    // Iteration functions.  The reference runs three host loops (domain.hpp:116-172); here
+    // stream() and swap() only record that they were called and collide() launches the fused
+    // pull-stream + BGK + boundary sweep for one time step.
+    auto stream() -> void
+    {
+        if (streamed) throw std::logic_error("stream() called twice without collide()");
+        streamed = true;
+    }
+    auto swap() -> void
+    {
+        if (!streamed || swapped) throw std::logic_error("swap() must follow stream() (src/main.cpp:50-52 order)");
+        swapped = true;
+    }
+    auto collide() -> void
+    {
+        if (!streamed || !swapped)
+            throw std::logic_error("collide() must follow stream(); swap(); -- a stand-alone collide has no "
+                    "device implementation");
+        streamed = swapped = false;
+        step(1);
+    }
+
+    // --- extensions ---
+    // n fused time steps; asynchronous, later read-outs synchronise
+    auto step(std::uint64_t n) -> void
+    {
+        require_idle("step()");
+        push_mirror();
+        push_geometry();
+        if (slabs.size() == 1) {
+            device::check(lbm_b200_step(slabs[0].handle, n), "lbm_b200_step");
+        } else {
+            for (std::uint64_t t = 0; t < n; ++t)
+                for (auto& s : slabs) device::check(lbm_b200_step(s.handle, 1), "lbm_b200_step");
+        }
+        steps_done += n;
+        mirror_valid = false;
+    }
+    auto synchronize() const -> void
+    {
+        for (auto& s : slabs) device::check(lbm_b200_sync(s.handle), "lbm_b200_sync");
+    }
+    // density / velocity of the interior cells in z,y,x order (the loop of io/vtk.hpp:62-73),
+    // reduced on the device and copied back
+    auto macroscopic(double* rho, double* u) const -> void
+    {
+        require_idle("macroscopic()");
+        auto* self = const_cast<Domain*>(this);
+        self->push_mirror();
+        self->push_geometry();
+        for (auto& s : slabs) {
+            const std::size_t off = (s.z_first - 1) * xl * yl;
+            device::check(lbm_b200_macroscopic(s.handle, rho ? rho + off : nullptr, u ? u + 3 * off : nullptr),
+                    "lbm_b200_macroscopic");
+        }
+    }
+    auto gpu_count() const -> std::size_t { return slabs.size(); }
+    auto timesteps_done() const -> std::uint64_t { return steps_done; }
+    auto slab_handle(std::size_t i) const -> lbm_b200_t* { return slabs.at(i).handle; }
+
+    // Parallelization tools.  The reference's x-slab helper (domain.hpp:197-248) copies an
+    // x-interval into a new Domain and tags the cut faces with ParallelBoundary; nothing ever
+    // exchanges data across them.  Kept for interface compatibility (host-side copy through
+    // cell()); real multi-GPU runs use the built-in z-slab split instead.
+    auto create_subdomain(parallel::ParallelBoundary<lattice_model>& parallel_boundary,
+            std::size_t xstart, std::size_t xend, int rank, int number_of_ranks) const -> Domain_ptr<lattice_model>
+    {
+        if (!(xend > xstart)) throw std::out_of_range("create_subdomain: xend must exceed xstart");
+        const std::size_t new_xl = xend - xstart + 1;
+        auto sub = make_unique<Domain<lattice_model>>(new_xl, yl, zl,
+                const_cast<FluidCollision<lattice_model>&>(*collision), xo + rank * new_xl * xs, yo, zo, xs, ys, zs);
+        for (std::size_t z = 0; z < zl + 2; ++z)
+            for (std::size_t y = 0; y < yl + 2; ++y)
+                for (std::size_t x = xstart; x < xend; ++x)
+                    sub->cell(int(x - xstart + 1), int(y), int(z)) = cell(int(x), int(y), int(z));
+        const bool leftmost = rank == 0, rightmost = rank == number_of_ranks - 1;
+        for (std::size_t z = 0; z < zl + 2; ++z)
+            for (std::size_t y = 0; y < yl + 2; ++y) {
+                if (leftmost) sub->cell(0, int(y), int(z)) = cell(0, int(y), int(z));
+                if (rightmost) sub->cell(int(new_xl + 1), int(y), int(z)) = cell(int(xl + 1), int(y), int(z));
+            }
+        sub->push_mirror();
+        if (!leftmost) sub->setBoundaryCondition(parallel_boundary, 0, 0, 0, yl + 1, 0, zl + 1);
+        if (!rightmost) sub->setBoundaryCondition(parallel_boundary, new_xl + 1, new_xl + 1, 0, yl + 1, 0, zl + 1);
+        return sub;
+    }
+};
+
+template <typename lattice_model>
+auto Cell<lattice_model>::has_fluid_vicinity(const Domain<lattice_model>& domain,
+        const uint_array<lattice_model::D>& position) const -> bool
+{
+    for (std::size_t q = 0; q < lattice_model::Q; ++q) {
+        const int nx = int(position[0]) + int(lattice_model::velocities[q][0]);
+        const int ny = int(position[1]) + int(lattice_model::velocities[q][1]);
+        const int nz = int(position[2]) + int(lattice_model::velocities[q][2]);
+        if (domain.in_bounds(nx, ny, nz) && domain.handler(nx, ny, nz)->is_fluid()) return true;
+    }
+    return false;
+}
+
+} // namespace lbm

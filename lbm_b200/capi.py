@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblbm_b200.so")
+# LBM_B200_LIB selects a tuning variant built by tools/build_variants.sh (same ABI, same sources)
+LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(_HERE, "liblbm_b200.so")
 
 FLUID, NOSLIP, MOVINGWALL, FREESLIP, OUTFLOW, INFLOW, PRESSURE, NULL, PARALLEL, PERIODIC = range(10)
 FAST, EXACT = 0, 1

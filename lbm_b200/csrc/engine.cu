@@ -114,6 +114,12 @@ struct lbm_b200 {
     long long peer_qstride[2] = { 0, 0 };
     long long peer_off[2] = { 0, 0 };
     void* peer_ipc_base[2] = { nullptr, nullptr };
+    void* peer_ipc_flags[2] = { nullptr, nullptr };
+    unsigned long long* d_flags = nullptr;          // [side]: sweeps completed by the neighbour on that side
+    unsigned long long* peer_flag[2] = { nullptr, nullptr };   // the neighbour's counter for us
+    unsigned long long halo_epoch = 0;              // sweeps completed since the peers were connected
+    int* d_halo_error = nullptr;
+    int* h_halo_error = nullptr;                    // pinned mirror
 
     size_t ncell() const { return (size_t) (g.xl + 2) * (g.yl + 2) * (g.zl + 2); }
     size_t field_bytes() const { return (size_t) g.qstride * Q * sizeof(double); }
@@ -257,7 +263,9 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers)
     p.bc = h->d_bc;
     p.g = g;
     p.z0 = z0;
-    int shift = 7;                       // 128 threads along x ...
+    int tshift = 0;
+    while ((1 << tshift) < LBM_SWEEP_THREADS) ++tshift;
+    int shift = tshift;                  // all threads along x ...
     while (shift > 5 && (1 << (shift - 1)) >= g.xl) --shift;   // ... unless the row is short
     p.bx_shift = shift;
     p.first = h->first ? 1 : 0;
@@ -273,12 +281,21 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers)
         p.dn_qstride = h->peer_qstride[LBM_B200_DOWN];
         p.dn_off = h->peer_off[LBM_B200_DOWN];
     }
-    const int bx = 1 << shift, by = 128 >> shift;
+    {
+        double vel[27 * 3];
+        lbm_b200_model(h->Q, vel, nullptr);
+        for (int q = 0; q < h->Q; ++q) {
+            const long long off = (long long) vel[3 * q + 2] * g.plane + (long long) vel[3 * q + 1] * g.P + (long long) vel[3 * q];
+            p.srcq[q] = p.src + (long long) q * g.qstride - off;
+            p.dstq[q] = p.dst + (long long) q * g.qstride;
+        }
+    }
+    const int bx = 1 << shift, by = LBM_SWEEP_THREADS >> shift;
     dim3 grid((g.xl + bx - 1) / bx, (g.yl + by - 1) / by, nz);
     dispatch_q(h->Q, [&](auto Qc) {
         constexpr int Q = decltype(Qc)::value;
-        if (h->exact) sweep_kernel<Q, true><<<grid, 128, 0, h->stream>>>(p);
-        else sweep_kernel<Q, false><<<grid, 128, 0, h->stream>>>(p);
+        if (h->exact) sweep_kernel<Q, true><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+        else sweep_kernel<Q, false><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
         return 0;
     });
     h->launches++;
@@ -299,6 +316,41 @@ int launch_ghost(lbm_b200* h)
     });
     h->launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+
+bool has_peers(const lbm_b200* h) { return h->peer_flag[0] || h->peer_flag[1]; }
+
+// see halo_wait_kernel / halo_signal_kernel
+int halo_wait(lbm_b200* h)
+{
+    if (!has_peers(h)) return 0;
+    int clock_khz = 1965000;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, h->device);
+    const long long timeout = (long long) clock_khz * 1000 * 20;    // ~20 s
+    halo_wait_kernel<<<1, 1, 0, h->stream>>>(h->peer_flag[LBM_B200_DOWN] ? h->d_flags + LBM_B200_DOWN : nullptr,
+                                             h->peer_flag[LBM_B200_UP] ? h->d_flags + LBM_B200_UP : nullptr,
+                                             h->halo_epoch, timeout, h->d_halo_error);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int halo_signal(lbm_b200* h)
+{
+    if (!has_peers(h)) return 0;
+    h->halo_epoch++;
+    halo_signal_kernel<<<1, 1, 0, h->stream>>>(h->peer_flag[LBM_B200_DOWN], h->peer_flag[LBM_B200_UP], h->halo_epoch);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int halo_check(lbm_b200* h)
+{
+    if (!has_peers(h)) return 0;
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, h->d_halo_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (err) return fail(LBM_B200_ETIMEOUT, "a neighbour slab did not complete its sweep within the hand-shake timeout");
     return 0;
 }
 
@@ -381,6 +433,10 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
     CUB(cudaMalloc(&h->d_mask, h->map_elems() * sizeof(uint32_t)));
     CUB(cudaMalloc(&h->d_kind, h->map_elems()));
     CUB(cudaMalloc(&h->d_bcid, h->map_elems() * sizeof(uint16_t)));
+    CUB(cudaMalloc(&h->d_flags, 2 * sizeof(unsigned long long)));
+    CUB(cudaMemset(h->d_flags, 0, 2 * sizeof(unsigned long long)));
+    CUB(cudaMalloc(&h->d_halo_error, sizeof(int)));
+    CUB(cudaMemset(h->d_halo_error, 0, sizeof(int)));
 #undef CUB
     h->h_kind.assign(h->ncell(), (uint8_t) LBM_B200_FLUID);   // domain.hpp:87-93
     h->h_bcid.assign(h->ncell(), 0);
@@ -440,8 +496,12 @@ int lbm_b200_destroy(lbm_b200_t* h)
     if (!h) return 0;
     DeviceGuard guard(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < 2; ++s) {
         if (h->peer_ipc_base[s]) cudaIpcCloseMemHandle(h->peer_ipc_base[s]);
+        if (h->peer_ipc_flags[s]) cudaIpcCloseMemHandle(h->peer_ipc_flags[s]);
+    }
+    if (h->d_flags) cudaFree(h->d_flags);
+    if (h->d_halo_error) cudaFree(h->d_halo_error);
     if (h->f[0]) cudaFree(h->f[0]);
     if (h->d_mask) cudaFree(h->d_mask);
     if (h->d_kind) cudaFree(h->d_kind);
@@ -672,8 +732,10 @@ int lbm_b200_step(lbm_b200_t* h, uint64_t n_steps)
     TRY(commit_geometry(h));
     CU(cudaEventRecord(h->ev_a, h->stream));
     for (uint64_t s = 0; s < n_steps; ++s) {
+        TRY(halo_wait(h));
         TRY(launch_sweep(h, 1, h->g.zl, true));
         TRY(launch_ghost(h));
+        TRY(halo_signal(h));
         finish_step(h);
     }
     CU(cudaEventRecord(h->ev_b, h->stream));
@@ -685,7 +747,7 @@ int lbm_b200_sync(lbm_b200_t* h)
 {
     GUARD(h);
     CU(cudaStreamSynchronize(h->stream));
-    return 0;
+    return halo_check(h);
 }
 
 int lbm_b200_elapsed_ms(lbm_b200_t* h, double* ms)
@@ -837,12 +899,18 @@ int lbm_b200_export(lbm_b200_t* h, void* blob)
     memcpy(p, &mh, 64);
     long long meta[4] = { h->g.qstride, h->g.plane, h->g.zl, h->Q };
     memcpy(p + 64, meta, sizeof meta);
+    cudaIpcMemHandle_t fh;
+    CU(cudaIpcGetMemHandle(&fh, h->d_flags));
+    memcpy(p + 128, &fh, 64);
     return 0;
 }
 
-static int connect_common(lbm_b200* h, int side, double* base, long long qstride, long long plane, long long zl, long long Q)
+static int connect_common(lbm_b200* h, int side, double* base, unsigned long long* nb_flags, long long qstride,
+                          long long plane, long long zl, long long Q)
 {
     if (Q != h->Q || plane != h->g.plane) return fail(LBM_B200_EINVAL, "neighbour slab has a different lattice or x-y shape");
+    // we are the neighbour's DOWN side when it is our UP side, and vice versa
+    h->peer_flag[side] = nb_flags + (side == LBM_B200_UP ? LBM_B200_DOWN : LBM_B200_UP);
     h->peer_f[side][0] = base;
     h->peer_f[side][1] = base + (size_t) qstride * Q;
     h->peer_qstride[side] = qstride;
@@ -864,7 +932,12 @@ int lbm_b200_connect(lbm_b200_t* h, int side, const void* blob)
     void* base = nullptr;
     CU(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
     h->peer_ipc_base[side] = base;
-    return connect_common(h, side, (double*) base, meta[0], meta[1], meta[2], meta[3]);
+    cudaIpcMemHandle_t fh;
+    memcpy(&fh, p + 128, 64);
+    void* fbase = nullptr;
+    CU(cudaIpcOpenMemHandle(&fbase, fh, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_ipc_flags[side] = fbase;
+    return connect_common(h, side, (double*) base, (unsigned long long*) fbase, meta[0], meta[1], meta[2], meta[3]);
 }
 
 int lbm_b200_connect_local(lbm_b200_t* h, int side, lbm_b200_t* nb)
@@ -879,7 +952,7 @@ int lbm_b200_connect_local(lbm_b200_t* h, int side, lbm_b200_t* nb)
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(LBM_B200_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
         cudaGetLastError();
     }
-    return connect_common(h, side, nb->f[0], nb->g.qstride, nb->g.plane, nb->g.zl, nb->Q);
+    return connect_common(h, side, nb->f[0], nb->d_flags, nb->g.qstride, nb->g.plane, nb->g.zl, nb->Q);
 }
 
 } // extern "C"

@@ -63,6 +63,11 @@ struct SweepParams {
     int wrap_z;        // periodic z is closed inside this slab
     double tau;
     double omega;      // 1/tau (fast mode)
+    // per-population base pointers with the pull offset folded in, so that a bulk
+    // load is ONE 64-bit multiply-add on a constant-bank operand:
+    //   srcq[q] = src + q*qstride - (cz*plane + cy*P + cx),   dstq[q] = dst + q*qstride
+    const double* srcq[27];
+    double* dstq[27];
     // optional remote copies of the slab-edge populations (peer ghost planes)
     double* up_dst;    // receives c_z=+1 populations of plane z = zl
     double* dn_dst;    // receives c_z=-1 populations of plane z = 1
@@ -309,14 +314,42 @@ __device__ __forceinline__ int wrap1(int v, int l) { return v < 1 ? v + l : (v >
 // ---------------------------------------------------------------------------
 // K1: one thread per interior cell.  Bulk cells (mask == 0): Q coalesced loads,
 // BGK in registers, Q coalesced 128B-aligned stores -> 2*Q*8 bytes per update.
+// tuning knobs (defaults = the measured best, see profiles/)
+#ifndef LBM_SWEEP_THREADS
+#define LBM_SWEEP_THREADS 64
+#endif
+// resident blocks per SM the register allocator must allow, per lattice
+// (profiles/variants_r02.txt: 1024 resident threads/SM at 64 registers for D3Q15/19,
+//  768 at 80 registers for D3Q27 -- more registers lose occupancy, fewer spill)
+#ifndef LBM_MB15
+#define LBM_MB15 16
+#endif
+#ifndef LBM_MB19
+#define LBM_MB19 16
+#endif
+#ifndef LBM_MB27
+#define LBM_MB27 12
+#endif
+template <int Q> struct MinBlocks { static constexpr int value = Q == 15 ? LBM_MB15 : (Q == 19 ? LBM_MB19 : LBM_MB27); };
+#ifdef LBM_LOAD_CS
+#define LBM_LD(ptr) __ldcs(ptr)
+#else
+#define LBM_LD(ptr) (*(ptr))
+#endif
+#ifdef LBM_STORE_CS
+#define LBM_ST(ptr, v) __stcs(ptr, v)
+#else
+#define LBM_ST(ptr, v) (*(ptr) = (v))
+#endif
+
 template <int Q, bool EXACT>
-__global__ void __launch_bounds__(128) sweep_kernel(const SweepParams p)
+__global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_kernel(const SweepParams p)
 {
     using L = Lattice<Q>;
     const Layout& g = p.g;
     const int bx = 1 << p.bx_shift;
     const int x = 1 + blockIdx.x * bx + (threadIdx.x & (bx - 1));
-    const int y = 1 + blockIdx.y * (128 >> p.bx_shift) + (threadIdx.x >> p.bx_shift);
+    const int y = 1 + blockIdx.y * (LBM_SWEEP_THREADS >> p.bx_shift) + (threadIdx.x >> p.bx_shift);
     const int z = p.z0 + blockIdx.z;
     if (x > g.xl || y > g.yl) return;
     const int i = cell_at(g, x, y, z);
@@ -327,8 +360,7 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepParams p)
     if (m == 0) {
         static_for<Q>([&](auto I) {
             constexpr int q = decltype(I)::value;
-            const int s = i - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
-            f[q] = p.src[q * g.qstride + s];
+            f[q] = LBM_LD(p.srcq[q] + i);
         });
     } else {
         OwnMoments om;
@@ -357,7 +389,7 @@ __global__ void __launch_bounds__(128) sweep_kernel(const SweepParams p)
 
     static_for<Q>([&](auto I) {
         constexpr int q = decltype(I)::value;
-        p.dst[q * g.qstride + i] = f[q];
+        LBM_ST(p.dstq[q] + i, f[q]);
     });
     // slab edges: hand the populations that leave the slab to the neighbour
     if (p.up_dst != nullptr && z == g.zl) {
@@ -569,6 +601,41 @@ __global__ void equilibrium_kernel(const double* __restrict__ rho, const double*
         constexpr int q = decltype(I)::value;
         field[q * g.qstride + i] = feq_exact<Q, q>(r, ux, uy, uz, uut);
     });
+}
+
+// ---------------------------------------------------------------------------
+// K4: slab hand-shake for direct peer stores.  Each slab owns two 64-bit arrival
+// counters (one per side) that the neighbour on that side bumps, with system
+// scope, after its sweep has stored its leaving populations into our ghost plane.
+// Before sweep number n+1 a slab waits until both neighbours have completed n
+// sweeps: that orders "their halo stores landed" (read-after-write) as well as
+// "they no longer read the buffer we are about to overwrite" (write-after-read).
+__global__ void halo_signal_kernel(unsigned long long* peer_flag_a, unsigned long long* peer_flag_b,
+                                   unsigned long long epoch)
+{
+    __threadfence_system();
+    if (peer_flag_a) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag_a), "l"(epoch) : "memory");
+    if (peer_flag_b) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag_b), "l"(epoch) : "memory");
+}
+
+__global__ void halo_wait_kernel(const unsigned long long* flag_a, const unsigned long long* flag_b,
+                                 unsigned long long epoch, long long timeout_cycles, int* error_word)
+{
+    const long long t0 = clock64();
+    const unsigned long long* flags[2] = { flag_a, flag_b };
+    for (int k = 0; k < 2; ++k) {
+        if (!flags[k]) continue;
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags[k]) : "memory");
+            if (v >= epoch) break;
+            if (clock64() - t0 > timeout_cycles) {   // never hang the GPU on a lost neighbour
+                *error_word = 1;
+                return;
+            }
+            __nanosleep(200);
+        }
+    }
 }
 
 // copy one x-y plane of selected populations (halo unpack / pack)

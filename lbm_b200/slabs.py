@@ -14,7 +14,10 @@ Transports
           interior planes are swept on the compute stream.
   "p2p"   the sweep kernel itself stores the leaving populations into the
           neighbour's ghost planes through CUDA-IPC peer mappings over NVLink
-          (fused sweep + exchange); a per-step barrier orders the buffer reuse.
+          (fused sweep + exchange); per-side arrival counters in device memory,
+          bumped with system-scope release stores and awaited by a one-thread
+          kernel in front of the next sweep, order the buffer reuse -- no host
+          synchronisation inside the time loop.
 """
 import os
 
@@ -141,23 +144,98 @@ class SlabRunner:
             self.dom.connect(DOWN, blobs[self.down])
         dist.barrier(group=self.group)
 
-    def _step_p2p(self):
-        import torch.distributed as dist
+    def _step_p2p(self, n):
         # the sweep stores the leaving populations straight into the neighbours' ghost planes of the
-        # buffer being written; the barrier orders "my writes landed / your reads finished"
-        self.dom.step(1)
-        self.stream.synchronize()
-        dist.barrier(group=self.group)
+        # buffer being written; the library's device-side hand-shake orders the buffer reuse
+        self.dom.step(n)
 
     # ---- public ----------------------------------------------------------------------
     def step(self, n=1):
         if self.transport == "none":
             self.dom.step(n)
             return
-        fn = self._step_nccl if self.transport == "nccl" else self._step_p2p
+        if self.transport == "p2p":
+            self._step_p2p(n)
+            return
         with self.torch.cuda.stream(self.stream):
             for _ in range(n):
-                fn()
+                self._step_nccl()
+
+    def sync(self):
+        self.dom.sync()
 
     def close(self):
         self.dom.close()
+
+
+class LocalSlabStack:
+    """N z-slabs driven from ONE process (what the C++ Domain does for `gpus = N`): slabs may sit on
+    different GPUs (peer access over NVLink) or, for testing the exchange logic on a single GPU, on
+    the same device."""
+
+    def __init__(self, Q, xl, yl, zl, tau, boxes, n_slabs, devices=None, exact=False, fluid_mask=None,
+                 periodic_z=False):
+        import numpy as np
+        self.np = np
+        self.Q, self.xl, self.yl, self.zl = Q, xl, yl, zl
+        self.ranges = partition(zl, n_slabs)
+        devices = devices or [0] * n_slabs
+        self.slabs = [capi.Domain(Q, xl, yl, zl, tau, device=devices[r], z_first=zf, zl_local=nz, exact=exact)
+                      for r, (zf, nz) in enumerate(self.ranges)]
+        for (zf, nz), s in zip(self.ranges, self.slabs):
+            if fluid_mask is not None:
+                m = np.asarray(fluid_mask, dtype=np.uint8).reshape(zl, yl, xl)
+                s.set_fluid_mask(m[zf - 1:zf - 1 + nz])
+            if boxes:
+                s.set_boxes(boxes)
+        for r in range(n_slabs):
+            down, up = neighbours(r, n_slabs, periodic_z)
+            if up is not None:
+                self.slabs[r].connect_local(UP, self.slabs[up])
+            if down is not None:
+                self.slabs[r].connect_local(DOWN, self.slabs[down])
+
+    def upload(self, f):
+        """f: [(xl+2)(yl+2)(zl+2), Q] global AoS; every slab gets its planes plus both ghost planes"""
+        np = self.np
+        plane = (self.xl + 2) * (self.yl + 2)
+        f = np.asarray(f).reshape(self.zl + 2, plane, self.Q)
+        for (zf, nz), s in zip(self.ranges, self.slabs):
+            s.upload(np.ascontiguousarray(f[zf - 1:zf + nz + 1]))
+
+    def step(self, n=1):
+        for _ in range(n):
+            for s in self.slabs:
+                s.step(1)
+
+    def sync(self):
+        for s in self.slabs:
+            s.sync()
+
+    def download(self):
+        """global AoS populations; interface ghost planes are taken from their owners"""
+        np = self.np
+        plane = (self.xl + 2) * (self.yl + 2)
+        out = np.empty((self.zl + 2, plane, self.Q))
+        self.sync()
+        for i, ((zf, nz), s) in enumerate(zip(self.ranges, self.slabs)):
+            loc = s.download().reshape(nz + 2, plane, self.Q)
+            lo = 0 if i == 0 else 1
+            hi = nz + 2 if i == len(self.slabs) - 1 else nz + 1
+            out[zf - 1 + lo:zf - 1 + hi] = loc[lo:hi]
+        return out.reshape(-1, self.Q)
+
+    def macroscopic(self):
+        np = self.np
+        rho = np.empty((self.zl, self.yl, self.xl))
+        u = np.empty((self.zl, self.yl, self.xl, 3))
+        self.sync()
+        for (zf, nz), s in zip(self.ranges, self.slabs):
+            r, v = s.macroscopic()
+            rho[zf - 1:zf - 1 + nz] = r
+            u[zf - 1:zf - 1 + nz] = v
+        return rho, u
+
+    def close(self):
+        for s in self.slabs:
+            s.close()

@@ -1,0 +1,109 @@
+"""Multi-slab parity: an N-slab run must equal the single-domain run BITWISE (the split changes no
+arithmetic).  Logical slabs on one GPU exercise the same peer-store + hand-shake code that
+runs across GPUs; the torchrun tests need >= 2 devices and skip otherwise."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import cases
+
+pytestmark = pytest.mark.gpu
+TAU = 0.6
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def single(Q, case, steps, exact=True):
+    from lbm_b200 import capi
+    with capi.Domain(Q, case["xl"], case["yl"], case["zl"], TAU, exact=exact) as d:
+        if case.get("fluid_mask") is not None:
+            d.set_fluid_mask(case["fluid_mask"])
+        if case["boxes"]:
+            d.set_boxes(case["boxes"])
+        if case.get("f_init") is not None:
+            d.upload(case["f_init"])
+        d.step(steps)
+        return d.download(), d.macroscopic()
+
+
+def stacked(Q, case, steps, n_slabs, exact=True):
+    from lbm_b200.slabs import LocalSlabStack
+    st = LocalSlabStack(Q, case["xl"], case["yl"], case["zl"], TAU, case["boxes"], n_slabs, exact=exact,
+                        fluid_mask=case.get("fluid_mask"))
+    try:
+        if case.get("f_init") is not None:
+            st.upload(case["f_init"])
+        st.step(steps)
+        return st.download(), st.macroscopic()
+    finally:
+        st.close()
+
+
+def fluid_rows(case, Q):
+    kind = O.oracle().run(Q, case["xl"], case["yl"], case["zl"], TAU, case["boxes"], 0,
+                          fluid_mask=case.get("fluid_mask"), want=("kind",))["kind"]
+    return kind == O.FLUID
+
+
+@pytest.mark.parametrize("Q", [15, 19, 27])
+@pytest.mark.parametrize("n_slabs", [2, 3])
+def test_cavity_slabs_equal_single_domain(Q, n_slabs):
+    case = dict(xl=12, yl=10, zl=13, boxes=O.cavity_boxes(12, 10, 13))
+    f1, (rho1, u1) = single(Q, case, 40)
+    fn, (rhon, un) = stacked(Q, case, 40, n_slabs)
+    fl = fluid_rows(case, Q)
+    assert np.array_equal(fn[fl], f1[fl])
+    assert np.array_equal(rhon, rho1) and np.array_equal(un, u1)
+
+
+@pytest.mark.parametrize("Q", [19, 27])
+def test_channel_with_obstacle_across_the_cut(Q):
+    # the no-slip block spans z = 3..8, the cuts of a 4-slab split of zl = 12 fall at 3|4, 6|7, 9|10
+    case = cases.channel(20, 8, 12, block=(6, 9, 2, 5, 3, 8))
+    f1, (rho1, u1) = single(Q, case, 50)
+    fn, (rhon, un) = stacked(Q, case, 50, 4)
+    fl = fluid_rows(case, Q)
+    assert np.array_equal(fn[fl], f1[fl])
+    # density/velocity of FLUID interior cells (obstacle cells next to a cut are not materialised
+    # across slabs)
+    inner = cases.interior_index(case["xl"], case["yl"], case["zl"])
+    sel = fl[inner].reshape(rho1.shape)
+    assert np.array_equal(rhon[sel], rho1[sel]) and np.array_equal(un[sel], u1[sel])
+
+
+def test_fast_mode_slabs_equal_single_domain_bitwise():
+    case = dict(xl=16, yl=16, zl=16, boxes=O.cavity_boxes(16, 16, 16))
+    f1, _ = single(19, case, 30, exact=False)
+    fn, _ = stacked(19, case, 30, 2, exact=False)
+    fl = fluid_rows(case, 19)
+    assert np.array_equal(fn[fl], f1[fl])
+
+
+def test_random_state_upload_slabs():
+    Q = 19
+    case = cases.channel(14, 7, 9, block=(4, 6, 2, 4, 2, 6))
+    rng = np.random.default_rng(7)
+    case["f_init"] = rng.random(((14 + 2) * (7 + 2) * (9 + 2), Q)) * 0.1 + 0.05
+    f1, _ = single(Q, case, 12)
+    fn, _ = stacked(Q, case, 12, 3)
+    fl = fluid_rows(case, Q)
+    assert np.array_equal(fn[fl], f1[fl])
+
+
+def _torchrun(n, *args):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")] + list(args)
+    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+
+
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+def test_two_processes_two_gpus(transport):
+    from lbm_b200 import capi
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    r = _torchrun(2, "--transport", transport)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MULTI_GPU_CHECK OK" in r.stdout
