@@ -113,7 +113,7 @@ def velocity_index(Q, u, v, w):
 
 
 def _boxes_arrays(boxes):
-    """boxes: list of (kind, v3, rho, (x0,xE,y0,yE,z0,zE)) as tests/_oracle.py builds them."""
+    """boxes: list of (kind, v3, rho, (x0,xE,y0,yE,z0,zE)) (the box-list format the tests use)."""
     n = len(boxes)
     ext = np.zeros((max(n, 1), 6), dtype=np.uint64)
     tab = (Bc * max(n, 1))()
