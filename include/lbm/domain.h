@@ -76,6 +76,13 @@ class Domain
     std::vector<const Collision<lattice_model>*> handlers;
     std::vector<std::uint16_t> handler_id;      // per cell, Domain::idx order
     bool geometry_dirty { true };
+    // set_nonfluid_cells_nullcollide() tags the collide field only (domain.hpp:108-109 goes through
+    // cell()), so in the reference a buried solid cell reports NullCollision on even and its
+    // original handler on odd step counts after the call.  No effect on any population; kept so
+    // that get_collision_handler() agrees.  null_original[i] = id before tagging, NOT_TAGGED else.
+    static constexpr std::uint16_t NOT_TAGGED = 0xFFFF;
+    std::vector<std::uint16_t> null_original;
+    std::uint64_t null_tagged_at { 0 };
 
     // host mirror behind cell()
     mutable Lattice_field<lattice_model> mirror;
@@ -84,6 +91,17 @@ class Domain
 
     bool streamed { false }, swapped { false };
     std::uint64_t steps_done { 0 };
+
+    std::uint16_t reported_id(std::size_t i) const
+    {
+        if (!null_original.empty() && null_original[i] != NOT_TAGGED && ((steps_done - null_tagged_at) & 1))
+            return null_original[i];
+        return handler_id[i];
+    }
+    void untag(std::size_t i)
+    {
+        if (!null_original.empty()) null_original[i] = NOT_TAGGED;
+    }
 
     std::size_t plane_cells() const { return (xl + 2) * (yl + 2); }
     std::size_t all_cells() const { return plane_cells() * (zl + 2); }
@@ -139,7 +157,7 @@ class Domain
                     std::memcpy(dst.data(), buf.data() + (p * plane_cells() + c) * Q, Q * sizeof(double));
                 }
         }
-        for (std::size_t i = 0; i < mirror.size(); ++i) mirror[i].set_collision_handler(handlers[handler_id[i]]);
+        for (std::size_t i = 0; i < mirror.size(); ++i) mirror[i].set_collision_handler(handlers[reported_id(i)]);
         mirror_valid = true;
         mirror_dirty = false;
     }
@@ -151,8 +169,9 @@ class Domain
         // handlers may have been changed through Cell::set_collision_handler
         for (std::size_t i = 0; i < mirror.size(); ++i) {
             const auto* h = mirror[i].get_collision_handler();
-            if (h != handlers[handler_id[i]]) {
+            if (h != handlers[reported_id(i)]) {
                 handler_id[i] = intern(h);
+                untag(i);
                 geometry_dirty = true;
             }
         }
@@ -255,7 +274,7 @@ public:
     auto handler(int x, int y, int z) const -> const Collision<lattice_model>*
     {
         if (mirror_valid && mirror_dirty) return mirror[idx(x, y, z)].get_collision_handler();
-        return handlers[handler_id[idx(x, y, z)]];
+        return handlers[reported_id(std::size_t(idx(x, y, z)))];
     }
 
     // domain.hpp:101-113: interior non-fluid cells without any interior fluid neighbour get the
@@ -282,7 +301,12 @@ public:
                 }
         if (lonely.empty()) return;
         const std::uint16_t id = intern(&null_collision);
-        for (auto i : lonely) handler_id[i] = id;
+        if (null_original.empty()) null_original.assign(all_cells(), NOT_TAGGED);
+        null_tagged_at = steps_done;
+        for (auto i : lonely) {
+            if (handler_id[i] != id) null_original[i] = handler_id[i];
+            handler_id[i] = id;
+        }
         if (mirror_valid)
             for (auto i : lonely) mirror[i].set_collision_handler(&null_collision);
         geometry_dirty = true;
@@ -299,7 +323,10 @@ public:
         const std::uint16_t id = intern(&condition);
         for (auto z = z0; z <= zE; ++z)
             for (auto y = y0; y <= yE; ++y)
-                for (auto x = x0; x <= xE; ++x) handler_id[std::size_t(idx(int(x), int(y), int(z)))] = id;
+                for (auto x = x0; x <= xE; ++x) {
+                    handler_id[std::size_t(idx(int(x), int(y), int(z)))] = id;
+                    untag(std::size_t(idx(int(x), int(y), int(z))));
+                }
         if (mirror_valid)
             for (auto z = z0; z <= zE; ++z)
                 for (auto y = y0; y <= yE; ++y)
