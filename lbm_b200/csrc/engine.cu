@@ -97,6 +97,9 @@ struct lbm_b200 {
     std::vector<uint16_t> h_bcid;
     std::vector<lbm_b200_bc> h_bc;
     bool geom_dirty = true;
+    bool geom_unchecked = false;   // maps supplied as arrays, not validated yet
+    double* d_rho = nullptr;       // persistent read-out staging
+    double* d_u = nullptr;
     bool first = true;         // boundary cells hold host-visible (stored) values
     bool materialized = true;  // boundary cells of f[cur] hold the reference's values
     int wrap_z = 0;
@@ -182,33 +185,59 @@ int commit_geometry(lbm_b200* h)
         CU(cudaMemcpyAsync(h->d_bc, recs.data(), recs.size() * sizeof(BcRec), cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
-    // validate + ghost-fluid list + periodic z
-    std::vector<int> ghost;
-    bool periodic_z = false;
+    // validate (only maps that came from the caller as arrays; boxes were checked one by one)
     const int nb = (int) h->h_bc.size();
-    for (int z = 0; z < g.zl + 2; ++z)
-        for (int y = 0; y < g.yl + 2; ++y) {
-            const size_t row = ((size_t) z * (g.yl + 2) + y) * (g.xl + 2);
+    if (h->geom_unchecked) {
+        const size_t rows = (size_t) (g.zl + 2) * (g.yl + 2);
+        int bad = 0;
+        long long bad_at = -1;
+        #pragma omp parallel for schedule(static)
+        for (long long r = 0; r < (long long) rows; ++r) {
+            const int z = (int) (r / (g.yl + 2)), y = (int) (r % (g.yl + 2));
+            const size_t row = (size_t) r * (g.xl + 2);
             for (int x = 0; x < g.xl + 2; ++x) {
                 const int k = h->h_kind[row + x];
-                if (k >= K_COUNT) return fail(LBM_B200_EINVAL, "cell (%d,%d,%d): unknown kind %d", x, y, z, k);
-                if (k >= K_NOSLIP && k <= K_PRESSURE) {
+                int why = 0;
+                if (k >= K_COUNT) why = 1;
+                else if (k >= K_NOSLIP && k <= K_PRESSURE) {
                     const int id = h->h_bcid[row + x];
-                    if (id >= nb) return fail(LBM_B200_EINVAL, "cell (%d,%d,%d): bc id %d outside table of %d", x, y, z, id, nb);
-                    if (h->h_bc[id].kind != k)
-                        return fail(LBM_B200_EINVAL, "cell (%d,%d,%d): kind %d but table[%d].kind = %d", x, y, z, k, id, h->h_bc[id].kind);
+                    if (id >= nb) why = 2;
+                    else if (h->h_bc[id].kind != k) why = 3;
+                } else if (k == K_PERIODIC && x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1) why = 4;
+                if (why) {
+                    #pragma omp critical
+                    if (!bad) { bad = why; bad_at = (long long) (row + x); }
                 }
-                const bool zshell = (z == 0 && h->z_first == 1) || (z == g.zl + 1 && h->z_first + g.zl - 1 == h->zl_global);
-                const bool shell = x == 0 || x == g.xl + 1 || y == 0 || y == g.yl + 1 || zshell;
-                const bool interior = x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1;
-                if (shell && k == K_FLUID && ((z > 0 && z < g.zl + 1) || zshell)) ghost.push_back(cell_at(g, x, y, z));
-                if (k == K_PERIODIC) {
-                    if (interior) return fail(LBM_B200_EINVAL, "cell (%d,%d,%d): PERIODIC is a ghost-shell kind", x, y, z);
-                    if (z == 0 || z == g.zl + 1) periodic_z = true;
-                }
-                if (!shell && !interior) { /* interface ghost plane of a slab: replica of the neighbour */ }
             }
         }
+        if (bad) {
+            const long long x = bad_at % (g.xl + 2), y = (bad_at / (g.xl + 2)) % (g.yl + 2), z = bad_at / ((long long) (g.xl + 2) * (g.yl + 2));
+            const char* msg[] = { "", "unknown kind", "bc id outside the table", "kind differs from table[bc id].kind", "PERIODIC is a ghost-shell kind" };
+            return fail(LBM_B200_EINVAL, "cell (%lld,%lld,%lld): %s", x, y, z, msg[bad]);
+        }
+        h->geom_unchecked = false;
+    }
+    // ghost-shell cells that kept the fluid handler, and periodic z: only the shell is scanned
+    std::vector<int> ghost;
+    bool periodic_z = false;
+    const bool z_lo_shell = h->z_first == 1, z_hi_shell = h->z_first + g.zl - 1 == h->zl_global;
+    auto visit = [&](int x, int y, int z) {
+        const int k = h->h_kind[((size_t) z * (g.yl + 2) + y) * (g.xl + 2) + x];
+        if (k == K_FLUID) ghost.push_back(cell_at(g, x, y, z));
+        if (k == K_PERIODIC && (z == 0 || z == g.zl + 1)) periodic_z = true;
+    };
+    for (int z = 0; z < g.zl + 2; ++z) {
+        const bool zshell = (z == 0 && z_lo_shell) || (z == g.zl + 1 && z_hi_shell);
+        if ((z == 0 || z == g.zl + 1) && !zshell) continue;   // interface ghost plane: the neighbour's cells
+        for (int y = 0; y < g.yl + 2; ++y) {
+            if (zshell || y == 0 || y == g.yl + 1) {
+                for (int x = 0; x < g.xl + 2; ++x) visit(x, y, z);
+            } else {
+                visit(0, y, z);
+                visit(g.xl + 1, y, z);
+            }
+        }
+    }
     if (periodic_z && (h->z_first != 1 || g.zl != h->zl_global))
         periodic_z = false;   // closed by the slab ring exchange instead
     h->wrap_z = periodic_z ? 1 : 0;
@@ -508,6 +537,8 @@ int lbm_b200_destroy(lbm_b200_t* h)
     if (h->d_bcid) cudaFree(h->d_bcid);
     if (h->d_bc) cudaFree(h->d_bc);
     if (h->d_ghost) cudaFree(h->d_ghost);
+    if (h->d_rho) cudaFree(h->d_rho);
+    if (h->d_u) cudaFree(h->d_u);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -550,6 +581,7 @@ int lbm_b200_set_geometry(lbm_b200_t* h, const uint8_t* kind, const uint16_t* bc
     else h->h_bcid.assign(n, 0);
     h->h_bc.assign(table, table + n_table);
     h->geom_dirty = true;
+    h->geom_unchecked = true;
     h->materialized = false;
     return 0;
 }
@@ -777,9 +809,10 @@ int lbm_b200_macroscopic(lbm_b200_t* h, double* rho, double* u)
     TRY(materialize(h));
     const Layout& g = h->g;
     const size_t n = (size_t) g.xl * g.yl * g.zl;
-    double *d_rho = nullptr, *d_u = nullptr;
-    if (rho) CU(cudaMalloc(&d_rho, n * sizeof(double)));
-    if (u && cudaMalloc(&d_u, 3 * n * sizeof(double)) != cudaSuccess) { cudaFree(d_rho); cudaGetLastError(); return fail(LBM_B200_ENOMEM, "output staging allocation failed"); }
+    if (rho && !h->d_rho) CU(cudaMalloc(&h->d_rho, n * sizeof(double)));
+    if (u && !h->d_u) CU(cudaMalloc(&h->d_u, 3 * n * sizeof(double)));
+    double* d_rho = rho ? h->d_rho : nullptr;
+    double* d_u = u ? h->d_u : nullptr;
     dim3 grid((g.xl + 127) / 128, g.yl, g.zl);
     dispatch_q(h->Q, [&](auto Qc) {
         macroscopic_kernel<decltype(Qc)::value><<<grid, 128, 0, h->stream>>>(h->f[h->cur], g, d_rho, d_u);
@@ -790,8 +823,6 @@ int lbm_b200_macroscopic(lbm_b200_t* h, double* rho, double* u)
     if (e == cudaSuccess && rho) e = cudaMemcpyAsync(rho, d_rho, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && u) e = cudaMemcpyAsync(u, d_u, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_rho);
-    cudaFree(d_u);
     if (e != cudaSuccess) return fail(LBM_B200_ECUDA, "macroscopic read-out failed: %s", cudaGetErrorString(e));
     return 0;
 }

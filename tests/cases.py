@@ -63,33 +63,51 @@ def interior_index(xl, yl, zl):
     return (x + (xl + 2) * y + (xl + 2) * (yl + 2) * z).reshape(-1)
 
 
-def taylor_green(n, Q, U0=0.01, mode="xy"):
-    """rho,u on all (n+2)^3 cells (cell centres at i-1/2)."""
+def taylor_green(n, U0=0.01, mode="xy"):
+    """Taylor-Green initial state on all (n+2)^3 cells (cell centres at i-1/2).
+
+    Returns (rho, u, c) with c the decay constant: kinetic energy ~ exp(-c * nu * k^2 * t), k = 2 pi / n.
+      xy/yz/xz  2-D vortex in a coordinate plane, |k|^2 = 2 k^2          -> c = 4
+      diag      the 2-D vortex rotated by 45 degrees in the x-y plane, |k|^2 = 4 k^2 -> c = 8
+      3d        u = U0 sin kx cos ky cos kz, v = -U0 cos kx sin ky cos kz, w = 0, |k|^2 = 3 k^2 -> c = 6
+                (exact only as the initial decay rate; Re = U0/(k nu) is kept small)
+    """
     cs2 = 0.57735026919 ** 2
     k = 2 * np.pi / n
     idx = np.arange(n + 2) - 0.5
     Z, Y, X = np.meshgrid(idx, idx, idx, indexing="ij")
     u = np.zeros((n + 2, n + 2, n + 2, 3))
+    rho = np.ones_like(X)
     if mode == "3d":
         u[..., 0] = U0 * np.sin(k * X) * np.cos(k * Y) * np.cos(k * Z)
         u[..., 1] = -U0 * np.cos(k * X) * np.sin(k * Y) * np.cos(k * Z)
-        rho = 1 + U0 ** 2 / (16 * cs2) * (np.cos(2 * k * X) + np.cos(2 * k * Y)) * (np.cos(2 * k * Z) + 2)
+        c = 6.0
     elif mode == "diag":
-        # 2-D vortex in the plane spanned by (1,1,0)/sqrt2 and z, wave number k along each
-        A = (X + Y)
-        a, b = k * A, k * Z * 2
-        ka, kb = k * np.sqrt(2.0), 2 * k
-        # stream function psi = cos(a) cos(b): u_A = -dpsi/dZ, u_Z = dpsi/dA
-        uA = U0 * np.cos(a) * np.sin(b)
-        uZ = -U0 * (ka / kb) * np.sin(a) * np.cos(b)
-        u[..., 0] = uA / np.sqrt(2.0)
-        u[..., 1] = uA / np.sqrt(2.0)
-        u[..., 2] = uZ
-        rho = np.ones_like(X)
+        a, b = k * (X + Y), k * (X - Y)
+        ua = U0 * np.sin(a) * np.cos(b)
+        ub = -U0 * np.cos(a) * np.sin(b)
+        u[..., 0] = (ua + ub) / np.sqrt(2.0)
+        u[..., 1] = (ua - ub) / np.sqrt(2.0)
+        rho = 1 - U0 ** 2 / (4 * cs2) * (np.cos(2 * a) + np.cos(2 * b))
+        c = 8.0
     else:
-        a_ax, b_ax = {"xy": (X, Y), "yz": (Y, Z), "xz": (X, Z)}[mode]
+        A, B = {"xy": (X, Y), "yz": (Y, Z), "xz": (X, Z)}[mode]
         ia, ib = {"xy": (0, 1), "yz": (1, 2), "xz": (0, 2)}[mode]
-        u[..., ia] = U0 * np.sin(k * a_ax) * np.cos(k * b_ax)
-        u[..., ib] = -U0 * np.cos(k * a_ax) * np.sin(k * b_ax)
-        rho = 1 - U0 ** 2 / (4 * cs2) * (np.cos(2 * k * a_ax) + np.cos(2 * k * b_ax))
-    return rho, u
+        u[..., ia] = U0 * np.sin(k * A) * np.cos(k * B)
+        u[..., ib] = -U0 * np.cos(k * A) * np.sin(k * B)
+        rho = 1 - U0 ** 2 / (4 * cs2) * (np.cos(2 * k * A) + np.cos(2 * k * B))
+        c = 4.0
+    return rho, u, c
+
+
+def duct_profile(ny, nz, terms=60):
+    """Fully developed laminar velocity in a rectangular duct (walls half-way between the first/last fluid
+    cell and the wall cell: widths ny, nz lattice units, cell centres at j-1/2), normalised to mean 1."""
+    y = np.arange(1, ny + 1) - 0.5 - ny / 2.0      # centred coordinates
+    z = np.arange(1, nz + 1) - 0.5
+    a, b = ny / 2.0, float(nz)                      # y in [-a, a], z in [0, b]
+    Zz, Yy = np.meshgrid(z, y, indexing="ij")
+    w = np.zeros_like(Yy)
+    for m in range(1, 2 * terms, 2):
+        w += (1.0 / m ** 3) * (1 - np.cosh(m * np.pi * Yy / b) / np.cosh(m * np.pi * a / b)) * np.sin(m * np.pi * Zz / b)
+    return w / w.mean()
