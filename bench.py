@@ -302,9 +302,15 @@ def measure_e2e(torch, dist, capi, run, args, world, cells_per_step):
     t0 = time.perf_counter()
     # H2D: geometry (kind map) through the public call; boxes re-applied on top keep the bc ids
     dom.set_boxes(cavity_boxes(dom.xl, dom.yl, dom.zl_global))
+    run.step(0)
+    run.sync()
+    t1 = time.perf_counter()
     run.step(args.steps)
+    run.sync()
+    t2 = time.perf_counter()
     capi._check(capi.lib.lbm_b200_macroscopic(dom._h, rho.data_ptr(), u.data_ptr()))
     torch.cuda.synchronize()
+    t3 = time.perf_counter()
     if world > 1:
         dist.barrier()
     dt = time.perf_counter() - t0
@@ -316,6 +322,8 @@ def measure_e2e(torch, dist, capi, run, args, world, cells_per_step):
     d2h = (rho.numel() + u.numel()) * 8 / args.steps
     return {"value": round(cells_per_step * args.steps / dt / 1e6, 1), "unit": "MLUPS",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "breakdown_ms": {"geometry_h2d": round(1e3 * (t1 - t0), 1), "steps": round(1e3 * (t2 - t1), 1),
+                             "macroscopic_d2h": round(1e3 * (t3 - t2), 1)},
             "protocol": "per rank: geometry maps H2D + %d steps + density/velocity D2H to pinned host memory, wall clock" % args.steps}
 
 

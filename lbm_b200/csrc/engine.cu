@@ -279,7 +279,7 @@ int commit_geometry(lbm_b200* h)
     return 0;
 }
 
-int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers)
+int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step = 1)
 {
     if (nz <= 0) return 0;
     const Layout& g = h->g;
@@ -292,6 +292,7 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers)
     p.bc = h->d_bc;
     p.g = g;
     p.z0 = z0;
+    p.z_step = z_step;
     int tshift = 0;
     while ((1 << tshift) < LBM_SWEEP_THREADS) ++tshift;
     int shift = tshift;                  // all threads along x ...
@@ -764,10 +765,20 @@ int lbm_b200_step(lbm_b200_t* h, uint64_t n_steps)
     TRY(commit_geometry(h));
     CU(cudaEventRecord(h->ev_a, h->stream));
     for (uint64_t s = 0; s < n_steps; ++s) {
-        TRY(halo_wait(h));
-        TRY(launch_sweep(h, 1, h->g.zl, true));
+        if (has_peers(h) && h->g.zl >= 3) {
+            // Only the two edge planes read ghost planes and feed the neighbours, so only they take
+            // part in the hand-shake; the interior sweep that follows gives every neighbour a whole
+            // step of slack before its next wait.
+            TRY(halo_wait(h));
+            TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1));
+            TRY(halo_signal(h));
+            TRY(launch_sweep(h, 2, h->g.zl - 2, false));
+        } else {
+            TRY(halo_wait(h));
+            TRY(launch_sweep(h, 1, h->g.zl, true));
+            TRY(halo_signal(h));
+        }
         TRY(launch_ghost(h));
-        TRY(halo_signal(h));
         finish_step(h);
     }
     CU(cudaEventRecord(h->ev_b, h->stream));
@@ -896,8 +907,8 @@ int lbm_b200_step_edges(lbm_b200_t* h)
     GUARD(h);
     if (h->edges_done) return fail(LBM_B200_ESTATE, "step_edges called twice");
     TRY(commit_geometry(h));
-    TRY(launch_sweep(h, 1, 1, true));
-    if (h->g.zl > 1) TRY(launch_sweep(h, h->g.zl, 1, true));
+    if (h->g.zl > 1) TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1));
+    else TRY(launch_sweep(h, 1, 1, true));
     h->edges_done = true;
     return 0;
 }

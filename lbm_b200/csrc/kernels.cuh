@@ -58,6 +58,7 @@ struct SweepParams {
     const BcRec* __restrict__ bc;
     Layout g;
     int z0;            // first plane swept by this launch
+    int z_step;        // plane stride between consecutive blockIdx.z (1, or zl-1 for the two edge planes)
     int bx_shift;      // log2(threads along x per block)
     int first;         // 1: boundary cells still hold host-visible values -> pull stored
     int wrap_z;        // periodic z is closed inside this slab
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
     const int bx = 1 << p.bx_shift;
     const int x = 1 + blockIdx.x * bx + (threadIdx.x & (bx - 1));
     const int y = 1 + blockIdx.y * (LBM_SWEEP_THREADS >> p.bx_shift) + (threadIdx.x >> p.bx_shift);
-    const int z = p.z0 + blockIdx.z;
+    const int z = p.z0 + blockIdx.z * p.z_step;
     if (x > g.xl || y > g.yl) return;
     const int i = cell_at(g, x, y, z);
     const uint32_t m = p.mask[i];

@@ -151,7 +151,7 @@ class SlabRunner:
 
     # ---- public ----------------------------------------------------------------------
     def step(self, n=1):
-        if self.transport == "none":
+        if self.transport == "none" or n == 0:
             self.dom.step(n)
             return
         if self.transport == "p2p":
