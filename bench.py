@@ -172,7 +172,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512, help="interior cells per edge, per GPU")
     ap.add_argument("--Q", type=int, default=19, choices=[15, 19, 27])
-    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--transport", default="p2p", choices=["nccl", "p2p"],
+                    help="p2p: the sweep stores leaving populations into the neighbour GPU's ghost plane (CUDA IPC over "
+                         "NVLink, device-side hand-shake); nccl: split-phase send/recv of the halo planes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--exact", action="store_true", help="bit-exact arithmetic (for curiosity; not the bench mode)")
@@ -205,8 +207,25 @@ def main():
     xl = yl = n
     zl_global = n * world                       # weak scaling: n^3 per GPU, slabs along z
     boxes = cavity_boxes(xl, yl, zl_global)
-    run = SlabRunner(Q, xl, yl, zl_global, TAU, boxes, rank=rank, world=world, device=local_rank,
-                     transport=args.transport, exact=args.exact)
+    transport = args.transport
+    try:
+        run = SlabRunner(Q, xl, yl, zl_global, TAU, boxes, rank=rank, world=world, device=local_rank,
+                         transport=transport, exact=args.exact)
+        ok = 1
+    except capi.LbmError as ex:          # e.g. CUDA IPC not permitted in this container
+        sys.stderr.write("rank %d: transport %s unavailable (%s)\n" % (rank, transport, ex))
+        ok = 0
+    if world > 1:
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            if transport == "nccl":
+                raise SystemExit("no usable halo transport")
+            transport = "nccl"           # another GPU transport, not a CPU path
+            run = SlabRunner(Q, xl, yl, zl_global, TAU, boxes, rank=rank, world=world, device=local_rank,
+                             transport=transport, exact=args.exact)
+    elif not ok:
+        raise SystemExit("cannot create the domain")
     dom = run.dom
     cells_per_step = xl * yl * zl_global        # interior cell updates per step, all ranks
 
@@ -273,7 +292,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": "lid-driven cavity D3Q%d BGK fp64 tau=0.6, %d^3 interior cells per GPU (%dx%dx%d global), "
-                            "z-slabs, %s" % (Q, n, xl, yl, zl_global, "1 GPU" if world == 1 else "transport=" + args.transport),
+                            "z-slabs, %s" % (Q, n, xl, yl, zl_global, "1 GPU" if world == 1 else "transport=" + transport),
                 "arithmetic": "exact" if args.exact else "fast",
                 "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed" % (2 * Q * 8 * (n + 2) ** 3 / 1e9),
                 "mlups_definition": "interior cell updates / s / 1e6",

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -117,7 +118,6 @@ struct lbm_b200 {
     long long peer_qstride[2] = { 0, 0 };
     long long peer_off[2] = { 0, 0 };
     void* peer_ipc_base[2] = { nullptr, nullptr };
-    void* peer_ipc_flags[2] = { nullptr, nullptr };
     unsigned long long* d_flags = nullptr;          // [side]: sweeps completed by the neighbour on that side
     unsigned long long* peer_flag[2] = { nullptr, nullptr };   // the neighbour's counter for us
     unsigned long long halo_epoch = 0;              // sweeps completed since the peers were connected
@@ -302,7 +302,8 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step = 1)
     p.wrap_z = h->wrap_z;
     p.tau = h->tau;
     p.omega = 1.0 / h->tau;
-    if (with_peers) {
+    static const bool debug_nostore = getenv("LBM_B200_DEBUG_NOSTORE") != nullptr;   // experiments only
+    if (with_peers && !debug_nostore) {
         const int dstbuf = 1 - h->cur;
         p.up_dst = h->peer_f[LBM_B200_UP][dstbuf];
         p.up_qstride = h->peer_qstride[LBM_B200_UP];
@@ -352,9 +353,11 @@ int launch_ghost(lbm_b200* h)
 bool has_peers(const lbm_b200* h) { return h->peer_flag[0] || h->peer_flag[1]; }
 
 // see halo_wait_kernel / halo_signal_kernel
+static bool debug_nosync() { static const bool v = getenv("LBM_B200_DEBUG_NOSYNC") != nullptr; return v; }
+
 int halo_wait(lbm_b200* h)
 {
-    if (!has_peers(h)) return 0;
+    if (!has_peers(h) || debug_nosync()) return 0;
     int clock_khz = 1965000;
     cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, h->device);
     const long long timeout = (long long) clock_khz * 1000 * 20;    // ~20 s
@@ -367,7 +370,7 @@ int halo_wait(lbm_b200* h)
 }
 int halo_signal(lbm_b200* h)
 {
-    if (!has_peers(h)) return 0;
+    if (!has_peers(h) || debug_nosync()) return 0;
     h->halo_epoch++;
     halo_signal_kernel<<<1, 1, 0, h->stream>>>(h->peer_flag[LBM_B200_DOWN], h->peer_flag[LBM_B200_UP], h->halo_epoch);
     h->launches++;
@@ -458,13 +461,14 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
     CUB(cudaEventCreate(&h->ev_a));
     CUB(cudaEventCreate(&h->ev_b));
     // one allocation for both lattices: a neighbour maps it with a single IPC handle
-    CUB(cudaMalloc(&h->f[0], 2 * h->field_bytes()));
+    // (IPC handles address whole allocations, so the hand-shake counters live in its tail)
+    CUB(cudaMalloc(&h->f[0], 2 * h->field_bytes() + 256));
     h->f[1] = h->f[0] + (size_t) h->g.qstride * Q;
+    h->d_flags = reinterpret_cast<unsigned long long*>(h->f[0] + 2 * (size_t) h->g.qstride * Q);
+    CUB(cudaMemset(h->d_flags, 0, 256));
     CUB(cudaMalloc(&h->d_mask, h->map_elems() * sizeof(uint32_t)));
     CUB(cudaMalloc(&h->d_kind, h->map_elems()));
     CUB(cudaMalloc(&h->d_bcid, h->map_elems() * sizeof(uint16_t)));
-    CUB(cudaMalloc(&h->d_flags, 2 * sizeof(unsigned long long)));
-    CUB(cudaMemset(h->d_flags, 0, 2 * sizeof(unsigned long long)));
     CUB(cudaMalloc(&h->d_halo_error, sizeof(int)));
     CUB(cudaMemset(h->d_halo_error, 0, sizeof(int)));
 #undef CUB
@@ -528,9 +532,7 @@ int lbm_b200_destroy(lbm_b200_t* h)
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     for (int s = 0; s < 2; ++s) {
         if (h->peer_ipc_base[s]) cudaIpcCloseMemHandle(h->peer_ipc_base[s]);
-        if (h->peer_ipc_flags[s]) cudaIpcCloseMemHandle(h->peer_ipc_flags[s]);
     }
-    if (h->d_flags) cudaFree(h->d_flags);
     if (h->d_halo_error) cudaFree(h->d_halo_error);
     if (h->f[0]) cudaFree(h->f[0]);
     if (h->d_mask) cudaFree(h->d_mask);
@@ -941,9 +943,6 @@ int lbm_b200_export(lbm_b200_t* h, void* blob)
     memcpy(p, &mh, 64);
     long long meta[4] = { h->g.qstride, h->g.plane, h->g.zl, h->Q };
     memcpy(p + 64, meta, sizeof meta);
-    cudaIpcMemHandle_t fh;
-    CU(cudaIpcGetMemHandle(&fh, h->d_flags));
-    memcpy(p + 128, &fh, 64);
     return 0;
 }
 
@@ -974,12 +973,8 @@ int lbm_b200_connect(lbm_b200_t* h, int side, const void* blob)
     void* base = nullptr;
     CU(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
     h->peer_ipc_base[side] = base;
-    cudaIpcMemHandle_t fh;
-    memcpy(&fh, p + 128, 64);
-    void* fbase = nullptr;
-    CU(cudaIpcOpenMemHandle(&fbase, fh, cudaIpcMemLazyEnablePeerAccess));
-    h->peer_ipc_flags[side] = fbase;
-    return connect_common(h, side, (double*) base, (unsigned long long*) fbase, meta[0], meta[1], meta[2], meta[3]);
+    unsigned long long* nb_flags = reinterpret_cast<unsigned long long*>((double*) base + 2 * meta[0] * meta[3]);
+    return connect_common(h, side, (double*) base, nb_flags, meta[0], meta[1], meta[2], meta[3]);
 }
 
 int lbm_b200_connect_local(lbm_b200_t* h, int side, lbm_b200_t* nb)

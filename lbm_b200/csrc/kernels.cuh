@@ -614,29 +614,32 @@ __global__ void equilibrium_kernel(const double* __restrict__ rho, const double*
 __global__ void halo_signal_kernel(unsigned long long* peer_flag_a, unsigned long long* peer_flag_b,
                                    unsigned long long epoch)
 {
+    // atomics are performed at the owning GPU's L2 (the point of coherence), so the value is visible
+    // to the neighbour's poll as soon as the NVLink transaction lands
     __threadfence_system();
-    if (peer_flag_a) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag_a), "l"(epoch) : "memory");
-    if (peer_flag_b) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag_b), "l"(epoch) : "memory");
+    if (peer_flag_a) atomicMax_system(peer_flag_a, epoch);
+    if (peer_flag_b) atomicMax_system(peer_flag_b, epoch);
 }
 
-__global__ void halo_wait_kernel(const unsigned long long* flag_a, const unsigned long long* flag_b,
+__global__ void halo_wait_kernel(unsigned long long* flag_a, unsigned long long* flag_b,
                                  unsigned long long epoch, long long timeout_cycles, int* error_word)
 {
     const long long t0 = clock64();
-    const unsigned long long* flags[2] = { flag_a, flag_b };
+    unsigned long long* flags[2] = { flag_a, flag_b };
     for (int k = 0; k < 2; ++k) {
         if (!flags[k]) continue;
         for (;;) {
-            unsigned long long v;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags[k]) : "memory");
+            // read-modify-write read: served by L2, never by a stale cached copy
+            const unsigned long long v = atomicAdd_system(flags[k], 0ull);
             if (v >= epoch) break;
             if (clock64() - t0 > timeout_cycles) {   // never hang the GPU on a lost neighbour
                 *error_word = 1;
                 return;
             }
-            __nanosleep(200);
+            __nanosleep(100);
         }
     }
+    __threadfence_system();
 }
 
 // copy one x-y plane of selected populations (halo unpack / pack)
