@@ -88,6 +88,7 @@ struct lbm_b200 {
     double* f[2] = { nullptr, nullptr };
     int cur = 0;               // f[cur] is the collide field
     uint32_t* d_mask = nullptr;
+    uint32_t* d_bits = nullptr;
     uint8_t* d_kind = nullptr;
     uint16_t* d_bcid = nullptr;
     BcRec* d_bc = nullptr;
@@ -258,8 +259,9 @@ int commit_geometry(lbm_b200* h)
         scatter_map_kernel<uint8_t><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(stage8, h->d_kind, g, 0);
         scatter_map_kernel<uint16_t><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(stage16, h->d_bcid, g, 0);
         CU(cudaMemsetAsync(h->d_mask, 0x80, h->map_elems() * sizeof(uint32_t), h->stream));
+        CU(cudaMemsetAsync(h->d_bits, 0, (h->map_elems() / 32 + 2) * sizeof(uint32_t), h->stream));
         dispatch_q(h->Q, [&](auto Qc) {
-            build_mask_kernel<decltype(Qc)::value><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->d_kind, h->d_mask, g);
+            build_mask_kernel<decltype(Qc)::value><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->d_kind, h->d_mask, h->d_bits, g);
             return 0;
         });
         h->launches += 3;
@@ -287,6 +289,7 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step = 1)
     p.src = h->f[h->cur];
     p.dst = h->f[1 - h->cur];
     p.mask = h->d_mask;
+    p.bits = h->d_bits;
     p.kind = h->d_kind;
     p.bcid = h->d_bcid;
     p.bc = h->d_bc;
@@ -467,6 +470,7 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
     h->d_flags = reinterpret_cast<unsigned long long*>(h->f[0] + 2 * (size_t) h->g.qstride * Q);
     CUB(cudaMemset(h->d_flags, 0, 256));
     CUB(cudaMalloc(&h->d_mask, h->map_elems() * sizeof(uint32_t)));
+    CUB(cudaMalloc(&h->d_bits, (h->map_elems() / 32 + 2) * sizeof(uint32_t)));
     CUB(cudaMalloc(&h->d_kind, h->map_elems()));
     CUB(cudaMalloc(&h->d_bcid, h->map_elems() * sizeof(uint16_t)));
     CUB(cudaMalloc(&h->d_halo_error, sizeof(int)));
@@ -536,6 +540,7 @@ int lbm_b200_destroy(lbm_b200_t* h)
     if (h->d_halo_error) cudaFree(h->d_halo_error);
     if (h->f[0]) cudaFree(h->f[0]);
     if (h->d_mask) cudaFree(h->d_mask);
+    if (h->d_bits) cudaFree(h->d_bits);
     if (h->d_kind) cudaFree(h->d_kind);
     if (h->d_bcid) cudaFree(h->d_bcid);
     if (h->d_bc) cudaFree(h->d_bc);

@@ -53,6 +53,7 @@ struct SweepParams {
     const double* __restrict__ src;   // collide field of the previous step
     double* __restrict__ dst;         // becomes the collide field
     const uint32_t* __restrict__ mask;
+    const uint32_t* __restrict__ bits;   // 1 bit per cell: mask != 0 (bulk cells never read `mask`)
     const uint8_t* __restrict__ kind;
     const uint16_t* __restrict__ bcid;
     const BcRec* __restrict__ bc;
@@ -354,6 +355,38 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
     const int z = p.z0 + blockIdx.z * p.z_step;
     if (x > g.xl || y > g.yl) return;
     const int i = cell_at(g, x, y, z);
+    // The link mask and the Q pulled populations are requested TOGETHER: every pull source of an
+    // interior cell exists in memory (ghost shell), so the loads need not wait for the mask.  One
+    // DRAM round trip per cell instead of two dependent ones; for the ~1 % of cells next to a wall
+    // the flagged directions are replaced afterwards.
+#ifndef LBM_NO_SPECULATIVE_PULL
+    const uint32_t word = p.bits[i >> 5];   // 1/8 byte per cell instead of the 4-byte mask
+    double f[Q];
+    static_for<Q>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        f[q] = LBM_LD(p.srcq[q] + i);
+    });
+    const uint32_t m = ((word >> (i & 31)) & 1u) ? p.mask[i] : 0u;
+    if (m & MASK_SKIP) return;
+    if (m != 0) {
+        OwnMoments om;
+        om.have = false;
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            if (m & (1u << q)) {
+                const int s = i - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
+                const int k = p.kind[s];
+                if (k == K_PERIODIC) {
+                    const int sx = wrap1(x - L::cx(q), g.xl), sy = wrap1(y - L::cy(q), g.yl);
+                    const int sz = p.wrap_z ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
+                    f[q] = p.src[q * g.qstride + cell_at(g, sx, sy, sz)];
+                } else if (!p.first) {   // first step: the stored value already pulled is the answer
+                    f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, p.bc + p.bcid[s], om);
+                }
+            }
+        });
+    }
+#else
     const uint32_t m = p.mask[i];
     if (m & MASK_SKIP) return;
 
@@ -385,6 +418,7 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
             }
         });
     }
+#endif
 
     bgk_collide<Q, EXACT>(f, p.tau, p.omega);
 
@@ -536,7 +570,8 @@ __global__ void fill_weights_kernel(double* __restrict__ field, long long qstrid
 
 // link mask: bit q set <=> the pull source X - c_q of interior fluid cell X is not fluid
 template <int Q>
-__global__ void build_mask_kernel(const uint8_t* __restrict__ kind, uint32_t* __restrict__ mask, const Layout g)
+__global__ void build_mask_kernel(const uint8_t* __restrict__ kind, uint32_t* __restrict__ mask,
+                                  uint32_t* __restrict__ bits, const Layout g)
 {
     const Tables<Q>& T = tables<Q>();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -555,6 +590,7 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ kind, uint32_t* __
         }
     }
     mask[i] = m;
+    if (m) atomicOr(&bits[i >> 5], 1u << (i & 31));   // bits zeroed by the caller
 }
 
 // dense (reference idx order) byte/short maps -> padded device maps, planes [z0, z0+nz)
