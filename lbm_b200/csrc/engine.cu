@@ -305,8 +305,7 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step = 1)
     p.wrap_z = h->wrap_z;
     p.tau = h->tau;
     p.omega = 1.0 / h->tau;
-    static const bool debug_nostore = getenv("LBM_B200_DEBUG_NOSTORE") != nullptr;   // experiments only
-    if (with_peers && !debug_nostore) {
+    if (with_peers) {
         const int dstbuf = 1 - h->cur;
         p.up_dst = h->peer_f[LBM_B200_UP][dstbuf];
         p.up_qstride = h->peer_qstride[LBM_B200_UP];
@@ -356,11 +355,9 @@ int launch_ghost(lbm_b200* h)
 bool has_peers(const lbm_b200* h) { return h->peer_flag[0] || h->peer_flag[1]; }
 
 // see halo_wait_kernel / halo_signal_kernel
-static bool debug_nosync() { static const bool v = getenv("LBM_B200_DEBUG_NOSYNC") != nullptr; return v; }
-
 int halo_wait(lbm_b200* h)
 {
-    if (!has_peers(h) || debug_nosync()) return 0;
+    if (!has_peers(h)) return 0;
     int clock_khz = 1965000;
     cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, h->device);
     const long long timeout = (long long) clock_khz * 1000 * 20;    // ~20 s
@@ -373,7 +370,7 @@ int halo_wait(lbm_b200* h)
 }
 int halo_signal(lbm_b200* h)
 {
-    if (!has_peers(h) || debug_nosync()) return 0;
+    if (!has_peers(h)) return 0;
     h->halo_epoch++;
     halo_signal_kernel<<<1, 1, 0, h->stream>>>(h->peer_flag[LBM_B200_DOWN], h->peer_flag[LBM_B200_UP], h->halo_epoch);
     h->launches++;

@@ -97,3 +97,50 @@ def test_command_line_driver_runs_a_scenario(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MLUPS:" in r.stdout and "Finished!" in r.stdout and "Reading scenario: \"Cavity64\"" in r.stdout
     assert sorted(os.listdir(tmp_path / "vtk")) == ["Cavity64.20.vts", "Cavity64.40.vts"]
+
+
+def test_legacy_vtk_fluid_mask_scenario(exe, tmp_path):
+    """domain from a legacy-VTK STRUCTURED_POINTS mask (io/vtk.hpp:94-157, pipe.xml style): solid cells
+    become no-slip cells (in both lattices, DESIGN.md deviation 1), then the <boundary> nodes apply."""
+    Q, steps = 19, 30
+    xl, yl, zl = 26, 9, 11
+    zz, yy, xx = np.meshgrid(np.arange(zl), np.arange(yl), np.arange(xl), indexing="ij")
+    mask = (((yy - (yl - 1) / 2) ** 2 / 16.0 + (zz - (zl - 1) / 2) ** 2 / 25.0) < 1.0).astype(np.uint8)
+    mask[:, :, 10:13] &= (yy[:, :, 10:13] > 2).astype(np.uint8)          # a baffle
+    vtk = tmp_path / "mask.vtk"
+    with open(vtk, "w") as f:
+        f.write("# vtk DataFile Version 2.0\nfluid mask\nASCII\n\nDATASET STRUCTURED_POINTS\n")
+        f.write("DIMENSIONS    %d   %d   %d\n\nORIGIN    -3.5   1.25   0.0\nSPACING   2.0   1.0   0.5\n\n" % (xl, yl, zl))
+        f.write("POINT_DATA   %d\nSCALARS inputfluidMask unsigned_char\nLOOKUP_TABLE default\n\n" % mask.size)
+        flat = mask.reshape(-1)
+        for i in range(0, flat.size, 40):
+            f.write(" ".join(str(v) for v in flat[i:i + 40]) + " \n")
+    xml = tmp_path / "pipe.xml"
+    xml.write_text('<?xml version="1.0" ?>\n<scenario name="Pipe flow">\n  <domain vtk-file="%s">\n'
+                   '    <boundary extent="z0" condition="noslip" />\n    <boundary extent="zmax" condition="noslip" />\n'
+                   '    <boundary extent="x0" condition="inflow" vx="0.03" vy="0" vz="0" />\n'
+                   '    <boundary extent="xmax" condition="outflow" />\n    <boundary extent="y0" condition="noslip" />\n'
+                   '    <boundary extent="ymax" condition="noslip" />\n  </domain>\n</scenario>\n' % vtk)
+    cfg = tmp_path / "run.cfg"
+    cfg.write_text("tau = 0.6\ntimesteps = %d\ntimesteps-per-plot = 0\noutput-dir = %s\nscenario-file = %s\n"
+                   % (steps, tmp_path / "vtk", xml))
+    env = dict(os.environ, LBM_B200_ARITHMETIC="exact")
+    dump = tmp_path / "dump.bin"
+    r = subprocess.run([exe, str(Q), str(cfg), str(steps), str(dump)], cwd=ROOT, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    dims, f0, f1, kinds, rho, u = read_dump(dump, steps)
+    assert dims == (xl, yl, zl, Q)
+    want = O.oracle().run(Q, xl, yl, zl, 0.6, O.channel_boxes(xl, yl, zl), steps, f_init=f0, fluid_mask=mask)
+    assert np.array_equal(kinds, want["kind"])
+    assert np.array_equal(f1, want["f"])
+    assert np.array_equal(rho, want["rho"]) and np.array_equal(u, want["u"])
+    # origin / spacing of the mask file reach the .vts point coordinates: spacing*i + origin - 1 (io/vtk.hpp:33)
+    blob = open(tmp_path / "vtk" / ("Pipe flow.%d.vts" % steps), "rb").read()
+    start = blob.index(b"_", blob.index(b"<AppendedData")) + 1
+    nv = struct.unpack("<Q", blob[start:start + 8])[0]
+    nd = struct.unpack("<Q", blob[start + 8 + nv:start + 16 + nv])[0]
+    pts_off = start + 16 + nv + nd
+    npts = struct.unpack("<Q", blob[pts_off:pts_off + 8])[0]
+    pts = np.frombuffer(blob, dtype=np.float64, count=npts // 8, offset=pts_off + 8).reshape(zl, yl, xl, 3)
+    assert np.array_equal(pts[0, 0, 0], [2.0 * 1 - 3.5 - 1, 1.0 * 1 + 1.25 - 1, 0.5 * 1 + 0.0 - 1])
+    assert np.array_equal(pts[-1, -1, -1], [2.0 * xl - 3.5 - 1, 1.0 * yl + 1.25 - 1, 0.5 * zl + 0.0 - 1])
