@@ -412,6 +412,20 @@ int materialize(lbm_b200* h)
     return 0;
 }
 
+// Geometry edits after time steps: first let the boundary cells of the OLD geometry take the values
+// the reference holds (its non-fluid pass ran after every step), then remember that the next stream
+// must pull stored values -- new boundary cells still carry their former fluid populations.
+int before_geometry_change(lbm_b200* h)
+{
+    if (h->steps > 0 && !h->geom_dirty) {
+        DeviceGuard guard(h->device);
+        if (!guard.ok) return fail(LBM_B200_ECUDA, "cannot select CUDA device %d", h->device);
+        TRY(materialize(h));
+    }
+    h->first = true;
+    return 0;
+}
+
 int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl_global, uint64_t z_first,
                   uint64_t zl_local, double tau, int device)
 {
@@ -580,6 +594,7 @@ int lbm_b200_set_geometry(lbm_b200_t* h, const uint8_t* kind, const uint16_t* bc
     if (!kind) return fail(LBM_B200_EINVAL, "kind map is null");
     if (n_table < 0 || n_table > 65535 || (n_table > 0 && !table)) return fail(LBM_B200_EINVAL, "bad boundary table");
     if (!bc_id && n_table > 1) return fail(LBM_B200_EINVAL, "bc_id map required for a table of %d handlers", n_table);
+    TRY(before_geometry_change(h));
     const size_t n = h->ncell();
     h->h_kind.assign(kind, kind + n);
     if (bc_id) h->h_bcid.assign(bc_id, bc_id + n);
@@ -595,6 +610,7 @@ int lbm_b200_set_boxes(lbm_b200_t* h, const uint64_t* boxes6, const lbm_b200_bc*
 {
     if (!h) return fail(LBM_B200_EINVAL, "null handle");
     if (n < 0 || (n > 0 && (!boxes6 || !table))) return fail(LBM_B200_EINVAL, "bad box list");
+    TRY(before_geometry_change(h));
     const Layout& g = h->g;
     for (int b = 0; b < n; ++b) {
         const uint64_t* e = boxes6 + 6 * b;
@@ -631,6 +647,7 @@ int lbm_b200_set_fluid_mask(lbm_b200_t* h, const uint8_t* mask)
     if (!h) return fail(LBM_B200_EINVAL, "null handle");
     if (!mask) return fail(LBM_B200_EINVAL, "mask is null");
     if (h->h_bc.size() >= 65535) return fail(LBM_B200_EINVAL, "more than 65535 boundary handlers");
+    TRY(before_geometry_change(h));
     const Layout& g = h->g;
     lbm_b200_bc solid{};
     solid.kind = LBM_B200_NOSLIP;

@@ -153,3 +153,59 @@ def test_download_upload_roundtrip_and_restart():
     assert_bitwise("restart", end_b, end)
     cpu = run_cpu(Q, case, 35)
     assert_bitwise("restart vs oracle", end, cpu["f"])
+
+
+@pytest.mark.parametrize("Q", [15, 19, 27])
+@pytest.mark.parametrize("dims", [(1, 1, 1), (1, 5, 3), (70, 3, 2), (2, 2, 2), (129, 7, 5), (33, 65, 4)])
+def test_degenerate_and_ragged_sizes_with_random_obstacles(Q, dims):
+    """edge cases: single-cell domains, rows shorter/longer than a block, sizes that are not multiples of
+    anything, random solid cells (every fluid cell is wall-adjacent somewhere), random initial state"""
+    xl, yl, zl = dims
+    rng = np.random.default_rng(xl * 10007 + yl * 101 + zl + Q)
+    mask = (rng.random((zl, yl, xl)) > 0.3).astype(np.uint8)
+    _, w = O.oracle().model(Q)
+    n_all = (xl + 2) * (yl + 2) * (zl + 2)
+    f0 = np.tile(w, (n_all, 1)) * (1 + 0.1 * rng.standard_normal((n_all, Q)))
+    case = dict(xl=xl, yl=yl, zl=zl, boxes=O.cavity_boxes(xl, yl, zl, (0.02, -0.01, 0.0)), fluid_mask=mask, f_init=f0)
+    steps = 7
+    cpu = run_cpu(Q, case, steps)
+    gpu = run_gpu(Q, case, steps, exact=True)
+    assert_bitwise("populations", gpu["f"], cpu["f"])
+    assert_bitwise("density", gpu["rho"], cpu["rho"])
+    assert_bitwise("velocity", gpu["u"], cpu["u"])
+
+
+def test_zero_steps_and_untouched_domain():
+    """empty input: no boundaries, no steps -> the reference's initial state (weights everywhere)"""
+    from lbm_b200 import capi
+    for Q in (15, 19, 27):
+        _, w = O.oracle().model(Q)
+        with capi.Domain(Q, 5, 4, 3, TAU, exact=True) as d:
+            d.step(0)
+            f = d.download()
+            assert d.steps_done() == 0
+            assert np.array_equal(f, np.tile(w, (f.shape[0], 1)))
+            # an uncovered ghost shell keeps the fluid handler and is collided in place (domain.hpp:147-155)
+            d.step(3)
+            cpu = O.oracle().run(Q, 5, 4, 3, TAU, [], 3)
+            assert_bitwise("no-boundary domain", d.download(), cpu["f"])
+
+
+def test_geometry_change_between_steps():
+    """setBoundaryCondition after some steps: the next stream pulls the stored values of the new boundary
+    cells, exactly like the reference"""
+    from lbm_b200 import capi
+    Q, n = 19, 10
+    base = O.cavity_boxes(n, n, n)
+    block = [(O.NOSLIP, (0.0, 0.0, 0.0), 1.0, (4, 6, 4, 6, 4, 6))]
+    with capi.Domain(Q, n, n, n, TAU, exact=True) as d:
+        d.set_boxes(base)
+        d.step(9)
+        mid = d.download()
+        d.set_boxes(block)
+        d.step(6)
+        got = d.download()
+    # oracle: restart from the state after 9 steps with the obstacle present from then on
+    cpu = O.oracle().run(Q, n, n, n, TAU, base + block, 6, f_init=mid)
+    fluid = cpu["kind"] == O.FLUID
+    assert_bitwise("after geometry change", got[fluid], cpu["f"][fluid])
