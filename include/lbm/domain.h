@@ -133,12 +133,23 @@ class Domain
         geometry_dirty = false;
     }
 
+    // boundary cells next to a slab cut need the neighbour slab's full edge plane for the read-back pass
+    void prepare_readback() const
+    {
+        if (slabs.size() < 2) return;
+        for (auto& s : slabs) device::check(lbm_b200_sync(s.handle), "lbm_b200_sync");
+        for (auto& s : slabs) device::check(lbm_b200_halo_push_all(s.handle), "lbm_b200_halo_push_all");
+        for (auto& s : slabs) device::check(lbm_b200_sync(s.handle), "lbm_b200_sync");
+        for (auto& s : slabs) device::check(lbm_b200_halo_pushed(s.handle), "lbm_b200_halo_pushed");
+    }
+
     // mirror <-> device
     void pull_mirror() const
     {
         if (mirror_valid) return;
         auto* self = const_cast<Domain*>(this);
         self->push_geometry();
+        prepare_readback();
         constexpr std::size_t Q = lattice_model::Q;
         if (mirror.empty()) mirror.assign(all_cells(), Cell<lattice_model>(collision));
         std::vector<double> buf;
@@ -384,6 +395,7 @@ public:
         auto* self = const_cast<Domain*>(this);
         self->push_mirror();
         self->push_geometry();
+        prepare_readback();
         for (auto& s : slabs) {
             const std::size_t off = (s.z_first - 1) * xl * yl;
             device::check(lbm_b200_macroscopic(s.handle, rho ? rho + off : nullptr, u ? u + 3 * off : nullptr),

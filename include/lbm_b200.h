@@ -189,6 +189,12 @@ int lbm_b200_step_finish(lbm_b200_t* h);    /* swap (after the exchange landed) 
 #define LBM_B200_EXPORT_BYTES 256
 int lbm_b200_export(lbm_b200_t* h, void* blob /*LBM_B200_EXPORT_BYTES*/);
 int lbm_b200_connect(lbm_b200_t* h, int side, const void* blob);
+/* Read-back across slab cuts: every slab pushes ALL populations of its edge planes into the
+ * neighbours' ghost planes (halo_push_all), the caller synchronises all slabs, then tells every slab
+ * (halo_pushed); the following download / macroscopic then materialises boundary cells next to a
+ * cut exactly like the reference's non-fluid pass (domain.hpp:157-165).  Needs connected peers. */
+int lbm_b200_halo_push_all(lbm_b200_t* h);
+int lbm_b200_halo_pushed(lbm_b200_t* h);
 /* same-process variant */
 int lbm_b200_connect_local(lbm_b200_t* h, int side, lbm_b200_t* neighbour);
 

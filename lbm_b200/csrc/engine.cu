@@ -111,6 +111,7 @@ struct lbm_b200 {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     bool timed = false;
     uint64_t steps = 0;
+    uint64_t full_halo_at = ~0ull;   // time level for which neighbours pushed their full edge planes
     uint64_t launches = 0;
     bool edges_done = false;   // split-phase state
 
@@ -400,10 +401,14 @@ int materialize(lbm_b200* h)
     TRY(commit_geometry(h));
     if (h->materialized) return 0;
     const Layout& g = h->g;
+    // interface ghost planes count as interior only if the neighbours' full planes were pushed
+    // there for this time level (lbm_b200_halo_push_all); otherwise links across a cut are skipped
+    const int lo_open = h->z_first != 1 && h->full_halo_at == h->steps;
+    const int hi_open = h->z_first + g.zl - 1 != h->zl_global && h->full_halo_at == h->steps;
     dispatch_q(h->Q, [&](auto Qc) {
         constexpr int Q = decltype(Qc)::value;
-        if (h->exact) materialize_kernel<Q, true><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, h->d_bcid, h->d_bc, g);
-        else materialize_kernel<Q, false><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, h->d_bcid, h->d_bc, g);
+        if (h->exact) materialize_kernel<Q, true><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, h->d_bcid, h->d_bc, g, lo_open, hi_open);
+        else materialize_kernel<Q, false><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, h->d_bcid, h->d_bc, g, lo_open, hi_open);
         return 0;
     });
     h->launches++;
@@ -947,6 +952,35 @@ int lbm_b200_step_finish(lbm_b200_t* h)
     if (!h->edges_done) return fail(LBM_B200_ESTATE, "step_finish before step_edges");
     h->edges_done = false;
     finish_step(h);
+    return 0;
+}
+
+// Read-back support for multi-slab domains: copy ALL Q populations of this slab's two edge planes
+// (current collide field) into the neighbours' ghost planes, so that their boundary pass can treat
+// cells next to the cut like the reference does.  The caller synchronises every slab (lbm_b200_sync
+// + a barrier across processes) between this call and the read-back, and calls it on every slab.
+int lbm_b200_halo_push_all(lbm_b200_t* h)
+{
+    GUARD(h);
+    const Layout& g = h->g;
+    const size_t bytes = (size_t) g.plane * sizeof(double);
+    for (int side = 0; side < 2; ++side) {
+        double* peer = h->peer_f[side][h->cur];
+        if (!peer) continue;
+        const int z_mine = side == LBM_B200_UP ? g.zl : 1;
+        for (int q = 0; q < h->Q; ++q)
+            CU(cudaMemcpyAsync(peer + (size_t) q * h->peer_qstride[side] + h->peer_off[side],
+                               h->f[h->cur] + (size_t) q * g.qstride + (size_t) z_mine * g.plane, bytes,
+                               cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return 0;
+}
+// tells this slab that its neighbours have pushed (and the caller has synchronised)
+int lbm_b200_halo_pushed(lbm_b200_t* h)
+{
+    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    h->full_halo_at = h->steps;
+    h->materialized = false;
     return 0;
 }
 

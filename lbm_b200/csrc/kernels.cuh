@@ -464,13 +464,17 @@ __global__ void ghost_fluid_kernel(double* __restrict__ field, long long qstride
 // the reference holds.  Reads fluid cells, writes non-fluid cells: no hazard.
 template <int Q, bool EXACT>
 __global__ void materialize_kernel(double* __restrict__ field, const uint8_t* __restrict__ kind,
-                                   const uint16_t* __restrict__ bcid, const BcRec* __restrict__ bc, const Layout g)
+                                   const uint16_t* __restrict__ bcid, const BcRec* __restrict__ bc, const Layout g,
+                                   const int z_lo_open, const int z_hi_open)
 {
+    // z_lo_open / z_hi_open: the ghost plane on that side is a slab interface whose cells are interior
+    // cells of the neighbour slab (their full populations were pushed here before this kernel)
     using L = Lattice<Q>;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int z = blockIdx.z;
     if (x > g.xl + 1) return;
+    if ((z == 0 && z_lo_open) || (z == g.zl + 1 && z_hi_open)) return;   // the neighbour's cells
     const int b = cell_at(g, x, y, z);
     const int k = kind[b];
     if (k < K_NOSLIP || k > K_PRESSURE) return;
@@ -478,7 +482,8 @@ __global__ void materialize_kernel(double* __restrict__ field, const uint8_t* __
     static_for<Q>([&](auto I) {
         constexpr int q = decltype(I)::value;
         const int nx = x + L::cx(q), ny = y + L::cy(q), nz = z + L::cz(q);
-        const bool inb = nx > 0 && nx < g.xl + 1 && ny > 0 && ny < g.yl + 1 && nz > 0 && nz < g.zl + 1;
+        const bool inb = nx > 0 && nx < g.xl + 1 && ny > 0 && ny < g.yl + 1
+                && (nz > 0 || z_lo_open) && (nz < g.zl + 1 || z_hi_open) && nz >= 0 && nz <= g.zl + 1;
         if (inb) {
             const int n = b + (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
             if (kind[n] == K_FLUID) {

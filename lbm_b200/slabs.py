@@ -164,6 +164,17 @@ class SlabRunner:
     def sync(self):
         self.dom.sync()
 
+    def prepare_readback(self):
+        """p2p transport only: full edge planes across the cuts before download()/macroscopic()"""
+        import torch.distributed as dist
+        self.dom.sync()
+        if self.transport == "p2p":
+            dist.barrier(group=self.group)
+            self.dom.halo_push_all()
+            self.dom.sync()
+            dist.barrier(group=self.group)
+            self.dom.halo_pushed()
+
     def close(self):
         self.dom.close()
 
@@ -212,12 +223,21 @@ class LocalSlabStack:
         for s in self.slabs:
             s.sync()
 
+    def prepare_readback(self):
+        """push full edge planes across the cuts so that boundary cells next to a cut read back exactly"""
+        self.sync()
+        for s in self.slabs:
+            s.halo_push_all()
+        self.sync()
+        for s in self.slabs:
+            s.halo_pushed()
+
     def download(self):
         """global AoS populations; interface ghost planes are taken from their owners"""
         np = self.np
         plane = (self.xl + 2) * (self.yl + 2)
         out = np.empty((self.zl + 2, plane, self.Q))
-        self.sync()
+        self.prepare_readback()
         for i, ((zf, nz), s) in enumerate(zip(self.ranges, self.slabs)):
             loc = s.download().reshape(nz + 2, plane, self.Q)
             lo = 0 if i == 0 else 1
@@ -229,7 +249,7 @@ class LocalSlabStack:
         np = self.np
         rho = np.empty((self.zl, self.yl, self.xl))
         u = np.empty((self.zl, self.yl, self.xl, 3))
-        self.sync()
+        self.prepare_readback()
         for (zf, nz), s in zip(self.ranges, self.slabs):
             r, v = s.macroscopic()
             rho[zf - 1:zf - 1 + nz] = r

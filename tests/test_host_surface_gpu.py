@@ -71,9 +71,8 @@ def test_reference_style_calls_match_oracle(exe, tmp_path, Q, name, gpus):
     assert np.array_equal(kinds, want["kind"])
     fluid = want["kind"] == O.FLUID
     assert np.array_equal(f1[fluid], want["f"][fluid])
-    if gpus == 1:
-        assert np.array_equal(f1, want["f"])          # boundary cells too (materialised on read-back)
-        assert np.array_equal(rho, want["rho"]) and np.array_equal(u, want["u"])
+    assert np.array_equal(f1, want["f"])              # boundary cells too (materialised on read-back)
+    assert np.array_equal(rho, want["rho"]) and np.array_equal(u, want["u"])
     # the .vts file holds the same density / velocity (raw appended Float64 blocks)
     vts = tmp_path / "vtk" / ("%s.%d.vts" % ("Step" if name == "step" else "Shear", steps))
     blob = open(vts, "rb").read()
