@@ -314,14 +314,14 @@ __device__ __forceinline__ double link_value(const double* __restrict__ src, con
 __device__ __forceinline__ int wrap1(int v, int l) { return v < 1 ? v + l : (v > l ? v - l : v); }
 
 // ---------------------------------------------------------------------------
-// K1: one thread per interior cell.  Bulk cells (mask == 0): Q coalesced loads,
-// BGK in registers, Q coalesced 128B-aligned stores -> 2*Q*8 bytes per update.
+// K1: one thread per interior cell.  Bulk cells: Q coalesced loads, BGK in registers,
+// Q coalesced 128B-aligned stores -> 2*Q*8 bytes per update.
 // tuning knobs (defaults = the measured best, see profiles/)
 #ifndef LBM_SWEEP_THREADS
 #define LBM_SWEEP_THREADS 64
 #endif
 // resident blocks per SM the register allocator must allow, per lattice
-// (profiles/variants_r02.txt: 1024 resident threads/SM at 64 registers for D3Q15/19,
+// (profiles/variants_r0*.txt: 1024 resident threads/SM at 64 registers for D3Q15/19,
 //  768 at 80 registers for D3Q27 -- more registers lose occupancy, fewer spill)
 #ifndef LBM_MB15
 #define LBM_MB15 16
@@ -344,30 +344,15 @@ template <int Q> struct MinBlocks { static constexpr int value = Q == 15 ? LBM_M
 #define LBM_ST(ptr, v) (*(ptr) = (v))
 #endif
 
+// Everything after the pull: replace the directions whose source is not fluid (link-wise boundary
+// values), collide, store, and hand slab-edge populations to the neighbour.  `f` holds the values
+// pulled speculatively for ALL directions; `m` is the cell's link mask (0 for bulk cells).
 template <int Q, bool EXACT>
-__global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_kernel(const SweepParams p)
+__device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q], const uint32_t m,
+                                            const int i, const int x, const int y, const int z)
 {
     using L = Lattice<Q>;
     const Layout& g = p.g;
-    const int bx = 1 << p.bx_shift;
-    const int x = 1 + blockIdx.x * bx + (threadIdx.x & (bx - 1));
-    const int y = 1 + blockIdx.y * (LBM_SWEEP_THREADS >> p.bx_shift) + (threadIdx.x >> p.bx_shift);
-    const int z = p.z0 + blockIdx.z * p.z_step;
-    if (x > g.xl || y > g.yl) return;
-    const int i = cell_at(g, x, y, z);
-    // The link mask and the Q pulled populations are requested TOGETHER: every pull source of an
-    // interior cell exists in memory (ghost shell), so the loads need not wait for the mask.  One
-    // DRAM round trip per cell instead of two dependent ones; for the ~1 % of cells next to a wall
-    // the flagged directions are replaced afterwards.
-#ifndef LBM_NO_SPECULATIVE_PULL
-    const uint32_t word = p.bits[i >> 5];   // 1/8 byte per cell instead of the 4-byte mask
-    double f[Q];
-    static_for<Q>([&](auto I) {
-        constexpr int q = decltype(I)::value;
-        f[q] = LBM_LD(p.srcq[q] + i);
-    });
-    const uint32_t m = ((word >> (i & 31)) & 1u) ? p.mask[i] : 0u;
-    if (m & MASK_SKIP) return;
     if (m != 0) {
         OwnMoments om;
         om.have = false;
@@ -386,39 +371,6 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
             }
         });
     }
-#else
-    const uint32_t m = p.mask[i];
-    if (m & MASK_SKIP) return;
-
-    double f[Q];
-    if (m == 0) {
-        static_for<Q>([&](auto I) {
-            constexpr int q = decltype(I)::value;
-            f[q] = LBM_LD(p.srcq[q] + i);
-        });
-    } else {
-        OwnMoments om;
-        om.have = false;
-        static_for<Q>([&](auto I) {
-            constexpr int q = decltype(I)::value;
-            const int s = i - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
-            if (m & (1u << q)) {
-                const int k = p.kind[s];
-                if (k == K_PERIODIC) {
-                    const int sx = wrap1(x - L::cx(q), g.xl), sy = wrap1(y - L::cy(q), g.yl);
-                    const int sz = p.wrap_z ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
-                    f[q] = p.src[q * g.qstride + cell_at(g, sx, sy, sz)];
-                } else if (p.first) {
-                    f[q] = p.src[q * g.qstride + s];           // first step: stored values
-                } else {
-                    f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, p.bc + p.bcid[s], om);
-                }
-            } else {
-                f[q] = p.src[q * g.qstride + s];
-            }
-        });
-    }
-#endif
 
     bgk_collide<Q, EXACT>(f, p.tau, p.omega);
 
@@ -426,7 +378,7 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
         constexpr int q = decltype(I)::value;
         LBM_ST(p.dstq[q] + i, f[q]);
     });
-    // slab edges: hand the populations that leave the slab to the neighbour
+    // slab edges: hand the populations that leave the slab to the neighbour (peer memory over NVLink)
     if (p.up_dst != nullptr && z == g.zl) {
         const int ip = i - z * g.plane;
         static_for<Q>([&](auto I) {
@@ -441,6 +393,31 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
             if constexpr (L::cz(q) == -1) p.dn_dst[q * p.dn_qstride + p.dn_off + ip] = f[q];
         });
     }
+}
+
+template <int Q, bool EXACT>
+__global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_kernel(const SweepParams p)
+{
+    const Layout& g = p.g;
+    const int bx = 1 << p.bx_shift;
+    const int x = 1 + blockIdx.x * bx + (threadIdx.x & (bx - 1));
+    const int y = 1 + blockIdx.y * (LBM_SWEEP_THREADS >> p.bx_shift) + (threadIdx.x >> p.bx_shift);
+    const int z = p.z0 + blockIdx.z * p.z_step;
+    if (x > g.xl || y > g.yl) return;
+    const int i = cell_at(g, x, y, z);
+    // The link bit and the Q pulled populations are requested TOGETHER: every pull source of an
+    // interior cell exists in memory (ghost shell), so the loads need not wait for the mask.  One
+    // DRAM round trip per cell instead of two dependent ones; for the ~1 % of cells next to a wall
+    // the flagged directions are replaced afterwards.  Bulk cells read 1/8 byte of map, not 4.
+    const uint32_t word = p.bits[i >> 5];
+    double f[Q];
+    static_for<Q>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        f[q] = LBM_LD(p.srcq[q] + i);
+    });
+    const uint32_t m = ((word >> (i & 31)) & 1u) ? p.mask[i] : 0u;
+    if (m & MASK_SKIP) return;
+    finish_cell<Q, EXACT>(p, f, m, i, x, y, z);
 }
 
 // K1g: ghost-shell cells that kept the fluid handler are BGK-collided in place in

@@ -156,7 +156,7 @@ def test_download_upload_roundtrip_and_restart():
 
 
 @pytest.mark.parametrize("Q", [15, 19, 27])
-@pytest.mark.parametrize("dims", [(1, 1, 1), (1, 5, 3), (70, 3, 2), (2, 2, 2), (129, 7, 5), (33, 65, 4)])
+@pytest.mark.parametrize("dims", [(1, 1, 1), (1, 5, 3), (70, 3, 2), (2, 2, 2), (129, 7, 5), (33, 65, 4), (256, 9, 3)])
 def test_degenerate_and_ragged_sizes_with_random_obstacles(Q, dims):
     """edge cases: single-cell domains, rows shorter/longer than a block, sizes that are not multiples of
     anything, random solid cells (every fluid cell is wall-adjacent somewhere), random initial state"""
