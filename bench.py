@@ -143,12 +143,11 @@ def run_reference_arm(args, rank):
         return
     Q, n = args.Q, 128
     threads = os.cpu_count() or 1
-    for _ in range(max(args.warmup, 0)):
-        cpu_reference_run(Q, n, 1, threads)
-    total_s, kind = 0.0, "port"
-    for _ in range(args.steps):
-        _, sec, kind = cpu_reference_run(Q, n, 1, threads)
-        total_s += sec
+    # W warm-up steps, then exactly K timed steps of the reference's own loop (one Domain, like src/main.cpp:48-61;
+    # the clock only runs inside stream(); swap(); collide();)
+    if args.warmup > 0:
+        cpu_reference_run(Q, n, args.warmup, threads)
+    _, total_s, kind = cpu_reference_run(Q, n, args.steps, threads)
     mlups = n ** 3 * args.steps / total_s / 1e6
     line = {
         "impl": "reference", "metric": "MLUPS", "value": round(mlups, 3), "unit": "MLUPS", "n_gpus": args.gpus,
