@@ -373,7 +373,7 @@ int halo_signal(lbm_b200* h)
 {
     if (!has_peers(h)) return 0;
     h->halo_epoch++;
-    halo_signal_kernel<<<1, 1, 0, h->stream>>>(h->peer_flag[LBM_B200_DOWN], h->peer_flag[LBM_B200_UP], h->halo_epoch);
+    halo_signal_kernel<<<1, 1, 0, h->stream>>>(h->peer_flag[LBM_B200_DOWN], h->peer_flag[LBM_B200_UP], h->halo_epoch, h->d_flags + 4);
     h->launches++;
     CU(cudaGetLastError());
     return 0;

@@ -630,13 +630,17 @@ __global__ void equilibrium_kernel(const double* __restrict__ rho, const double*
 // sweeps: that orders "their halo stores landed" (read-after-write) as well as
 // "they no longer read the buffer we are about to overwrite" (write-after-read).
 __global__ void halo_signal_kernel(unsigned long long* peer_flag_a, unsigned long long* peer_flag_b,
-                                   unsigned long long epoch)
+                                   unsigned long long epoch, unsigned long long* scratch)
 {
     // atomics are performed at the owning GPU's L2 (the point of coherence), so the value is visible
-    // to the neighbour's poll as soon as the NVLink transaction lands
+    // to the neighbour's poll as soon as the NVLink transaction lands.  The RETURNING form is used on
+    // purpose: it is a round trip, so this kernel only retires once the neighbour really has the
+    // value (a posted reduction may linger in the fabric until later traffic pushes it along).
     __threadfence_system();
-    if (peer_flag_a) atomicMax_system(peer_flag_a, epoch);
-    if (peer_flag_b) atomicMax_system(peer_flag_b, epoch);
+    unsigned long long seen = 0;
+    if (peer_flag_a) seen += atomicMax_system(peer_flag_a, epoch);
+    if (peer_flag_b) seen += atomicMax_system(peer_flag_b, epoch);
+    *scratch = seen;
 }
 
 __global__ void halo_wait_kernel(unsigned long long* flag_a, unsigned long long* flag_b,
