@@ -124,6 +124,9 @@ struct lbm_b200 {
     unsigned long long* peer_flag[2] = { nullptr, nullptr };   // the neighbour's counter for us
     unsigned long long halo_epoch = 0;              // sweeps completed since the peers were connected
     int* d_halo_error = nullptr;
+    int clock_khz = 1965000;
+    unsigned long long* d_trace = nullptr;         // LBM_B200_HALO_TRACE=<file prefix>: wait-kernel timestamps
+    static constexpr int TRACE_EPOCHS = 8192;
     int* h_halo_error = nullptr;                    // pinned mirror
 
     size_t ncell() const { return (size_t) (g.xl + 2) * (g.yl + 2) * (g.zl + 2); }
@@ -359,12 +362,13 @@ bool has_peers(const lbm_b200* h) { return h->peer_flag[0] || h->peer_flag[1]; }
 int halo_wait(lbm_b200* h)
 {
     if (!has_peers(h)) return 0;
-    int clock_khz = 1965000;
-    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, h->device);
-    const long long timeout = (long long) clock_khz * 1000 * 20;    // ~20 s
+    // (the clock rate is read once at creation: cudaDeviceGetAttribute(cudaDevAttrClockRate) is a
+    //  driver round trip of milliseconds and made the host the bottleneck when it ran every step)
+    const long long timeout = (long long) h->clock_khz * 1000 * 20;    // ~20 s
     halo_wait_kernel<<<1, 1, 0, h->stream>>>(h->peer_flag[LBM_B200_DOWN] ? h->d_flags + LBM_B200_DOWN : nullptr,
                                              h->peer_flag[LBM_B200_UP] ? h->d_flags + LBM_B200_UP : nullptr,
-                                             h->halo_epoch, timeout, h->d_halo_error);
+                                             h->halo_epoch, timeout, h->d_halo_error,
+                                             h->halo_epoch < lbm_b200::TRACE_EPOCHS ? h->d_trace : nullptr);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -489,8 +493,16 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
     CUB(cudaMalloc(&h->d_bits, (h->map_elems() / 32 + 2) * sizeof(uint32_t)));
     CUB(cudaMalloc(&h->d_kind, h->map_elems()));
     CUB(cudaMalloc(&h->d_bcid, h->map_elems() * sizeof(uint16_t)));
+    if (cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device) != cudaSuccess || h->clock_khz <= 0) {
+        cudaGetLastError();
+        h->clock_khz = 1965000;
+    }
     CUB(cudaMalloc(&h->d_halo_error, sizeof(int)));
     CUB(cudaMemset(h->d_halo_error, 0, sizeof(int)));
+    if (getenv("LBM_B200_HALO_TRACE")) {
+        CUB(cudaMalloc(&h->d_trace, 2 * lbm_b200::TRACE_EPOCHS * sizeof(unsigned long long)));
+        CUB(cudaMemset(h->d_trace, 0, 2 * lbm_b200::TRACE_EPOCHS * sizeof(unsigned long long)));
+    }
 #undef CUB
     h->h_kind.assign(h->ncell(), (uint8_t) LBM_B200_FLUID);   // domain.hpp:87-93
     h->h_bcid.assign(h->ncell(), 0);
@@ -550,6 +562,20 @@ int lbm_b200_destroy(lbm_b200_t* h)
     if (!h) return 0;
     DeviceGuard guard(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    if (h->d_trace) {   // diagnostic dump: "<prefix>.<device>.z<first plane>" with entry/exit ns per epoch
+        std::vector<unsigned long long> t(2 * lbm_b200::TRACE_EPOCHS);
+        cudaDeviceSynchronize();
+        if (cudaMemcpy(t.data(), h->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            const std::string path = std::string(getenv("LBM_B200_HALO_TRACE") ? getenv("LBM_B200_HALO_TRACE") : "halo_trace")
+                    + "." + std::to_string(h->device) + ".z" + std::to_string(h->z_first);
+            if (FILE* fp = fopen(path.c_str(), "w")) {
+                for (unsigned long long e = 0; e < h->halo_epoch && e < (unsigned long long) lbm_b200::TRACE_EPOCHS; ++e)
+                    fprintf(fp, "%llu %llu %llu\n", e, t[2 * e], t[2 * e + 1]);
+                fclose(fp);
+            }
+        }
+        cudaFree(h->d_trace);
+    }
     for (int s = 0; s < 2; ++s) {
         if (h->peer_ipc_base[s]) cudaIpcCloseMemHandle(h->peer_ipc_base[s]);
     }

@@ -644,8 +644,11 @@ __global__ void halo_signal_kernel(unsigned long long* peer_flag_a, unsigned lon
 }
 
 __global__ void halo_wait_kernel(unsigned long long* flag_a, unsigned long long* flag_b,
-                                 unsigned long long epoch, long long timeout_cycles, int* error_word)
+                                 unsigned long long epoch, long long timeout_cycles, int* error_word,
+                                 unsigned long long* trace)
 {
+    // optional trace (LBM_B200_HALO_TRACE): nanosecond timestamps of entry and exit per epoch
+    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[2 * epoch]));
     const long long t0 = clock64();
     unsigned long long* flags[2] = { flag_a, flag_b };
     for (int k = 0; k < 2; ++k) {
@@ -662,6 +665,7 @@ __global__ void halo_wait_kernel(unsigned long long* flag_a, unsigned long long*
         }
     }
     __threadfence_system();
+    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[2 * epoch + 1]));
 }
 
 // copy one x-y plane of selected populations (halo unpack / pack)
