@@ -171,10 +171,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512, help="interior cells per edge, per GPU")
     ap.add_argument("--Q", type=int, default=19, choices=[15, 19, 27])
-    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"],
-                    help="nccl (default: steadier at 8 GPUs, profiles/r01_scaling.txt): split-phase grouped send/recv of the "
-                         "halo planes overlapped with the interior sweep; p2p: the sweep stores leaving populations into the "
-                         "neighbour GPU's ghost plane (CUDA IPC over NVLink, device-side hand-shake)")
+    ap.add_argument("--transport", default="p2p", choices=["nccl", "p2p"],
+                    help="p2p (default): the sweep stores leaving populations into the neighbour GPU's ghost plane (CUDA IPC "
+                         "over NVLink, device-side hand-shake), falls back to nccl if IPC is unavailable; nccl: split-phase "
+                         "grouped send/recv of the halo planes overlapped with the interior sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--exact", action="store_true", help="bit-exact arithmetic (for curiosity; not the bench mode)")
