@@ -245,6 +245,8 @@ public:
 
     ~Domain()
     {
+        for (auto& s : slabs) lbm_b200_sync(s.handle);
+        for (auto& s : slabs) lbm_b200_disconnect(s.handle);
         for (auto& s : slabs) lbm_b200_destroy(s.handle);
     }
     Domain(const Domain&) = delete;

@@ -195,6 +195,8 @@ int lbm_b200_connect(lbm_b200_t* h, int side, const void* blob);
  * cut exactly like the reference's non-fluid pass (domain.hpp:157-165).  Needs connected peers. */
 int lbm_b200_halo_push_all(lbm_b200_t* h);
 int lbm_b200_halo_pushed(lbm_b200_t* h);
+/* drop the peer mappings again: call on every slab (after a sync / barrier) before any is destroyed */
+int lbm_b200_disconnect(lbm_b200_t* h);
 /* same-process variant */
 int lbm_b200_connect_local(lbm_b200_t* h, int side, lbm_b200_t* neighbour);
 

@@ -34,6 +34,7 @@ SYMBOLS = [
     "lbm_b200_halo_layout", "lbm_b200_halo_plane", "lbm_b200_dst_buffer",
     "lbm_b200_step_edges", "lbm_b200_step_interior", "lbm_b200_step_finish",
     "lbm_b200_export", "lbm_b200_connect", "lbm_b200_connect_local", "lbm_b200_halo_push_all", "lbm_b200_halo_pushed",
+    "lbm_b200_disconnect",
 ]
 
 
@@ -88,6 +89,7 @@ lib.lbm_b200_connect.argtypes = [_H, C.c_int, C.c_void_p]
 lib.lbm_b200_connect_local.argtypes = [_H, C.c_int, _H]
 lib.lbm_b200_halo_push_all.argtypes = [_H]
 lib.lbm_b200_halo_pushed.argtypes = [_H]
+lib.lbm_b200_disconnect.argtypes = [_H]
 
 
 def _check(rc):
@@ -283,6 +285,9 @@ class Domain:
 
     def connect_local(self, side, other):
         _check(lib.lbm_b200_connect_local(self._h, side, other._h))
+
+    def disconnect(self):
+        _check(lib.lbm_b200_disconnect(self._h))
 
     def halo_push_all(self):
         _check(lib.lbm_b200_halo_push_all(self._h))

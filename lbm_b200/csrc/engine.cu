@@ -125,6 +125,7 @@ struct lbm_b200 {
     unsigned long long halo_epoch = 0;              // sweeps completed since the peers were connected
     int* d_halo_error = nullptr;
     int clock_khz = 1965000;
+    long long pull_offset[27] = {};                 // c_z*plane + c_y*P + c_x per direction
     unsigned long long* d_trace = nullptr;         // LBM_B200_HALO_TRACE=<file prefix>: wait-kernel timestamps
     static constexpr int TRACE_EPOCHS = 8192;
     int* h_halo_error = nullptr;                    // pinned mirror
@@ -135,6 +136,13 @@ struct lbm_b200 {
 };
 
 namespace {
+
+// temporary device allocation that cannot leak on an early error return
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
 
 struct DeviceGuard {
     int prev = -1;
@@ -252,10 +260,11 @@ int commit_geometry(lbm_b200* h)
 
     // dense -> padded maps through a device staging copy
     {
-        uint8_t* stage8 = nullptr;
-        uint16_t* stage16 = nullptr;
-        CU(cudaMalloc(&stage8, n));
-        CU(cudaMalloc(&stage16, n * sizeof(uint16_t)));
+        DevBuf buf8, buf16;
+        CU(cudaMalloc(&buf8.p, n));
+        CU(cudaMalloc(&buf16.p, n * sizeof(uint16_t)));
+        uint8_t* stage8 = buf8.as<uint8_t>();
+        uint16_t* stage16 = buf16.as<uint16_t>();
         CU(cudaMemcpyAsync(stage8, h->h_kind.data(), n, cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(stage16, h->h_bcid.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemsetAsync(h->d_kind, K_NULL, h->map_elems(), h->stream));
@@ -271,8 +280,6 @@ int commit_geometry(lbm_b200* h)
         h->launches += 3;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(h->stream));
-        CU(cudaFree(stage8));
-        CU(cudaFree(stage16));
     }
     if (h->d_ghost) CU(cudaFree(h->d_ghost));
     h->d_ghost = nullptr;
@@ -318,14 +325,9 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step = 1)
         p.dn_qstride = h->peer_qstride[LBM_B200_DOWN];
         p.dn_off = h->peer_off[LBM_B200_DOWN];
     }
-    {
-        double vel[27 * 3];
-        lbm_b200_model(h->Q, vel, nullptr);
-        for (int q = 0; q < h->Q; ++q) {
-            const long long off = (long long) vel[3 * q + 2] * g.plane + (long long) vel[3 * q + 1] * g.P + (long long) vel[3 * q];
-            p.srcq[q] = p.src + (long long) q * g.qstride - off;
-            p.dstq[q] = p.dst + (long long) q * g.qstride;
-        }
+    for (int q = 0; q < h->Q; ++q) {
+        p.srcq[q] = p.src + (long long) q * g.qstride - h->pull_offset[q];
+        p.dstq[q] = p.dst + (long long) q * g.qstride;
     }
     const int bx = 1 << shift, by = LBM_SWEEP_THREADS >> shift;
     dim3 grid((g.xl + bx - 1) / bx, (g.yl + by - 1) / by, nz);
@@ -471,6 +473,12 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
     h->zl_global = (int) zl_global;
     h->z_first = (int) z_first;
     h->tau = tau;
+    {
+        double vel[27 * 3];
+        lbm_b200_model(Q, vel, nullptr);
+        for (int q = 0; q < Q; ++q)
+            h->pull_offset[q] = (long long) vel[3 * q + 2] * h->g.plane + (long long) vel[3 * q + 1] * h->g.P + (long long) vel[3 * q];
+    }
     *out = h;   // so that the caller can destroy on failure below
     DeviceGuard guard(device);
     if (!guard.ok) { lbm_b200_destroy(h); *out = nullptr; return fail(LBM_B200_ECUDA, "cannot select CUDA device %d", device); }
@@ -732,8 +740,9 @@ static int transfer_populations(lbm_b200* h, double* host, int layout, int field
     const size_t plane_vals = (size_t) (g.xl + 2) * (g.yl + 2) * Q;
     int chunk = (int) std::max<size_t>(1, ((size_t) 256 << 20) / (plane_vals * sizeof(double)));
     chunk = std::min(chunk, g.zl + 2);
-    double* stage = nullptr;
-    CU(cudaMalloc(&stage, plane_vals * chunk * sizeof(double)));
+    DevBuf stage_buf;
+    CU(cudaMalloc(&stage_buf.p, plane_vals * chunk * sizeof(double)));
+    double* stage = stage_buf.as<double>();
     int rc = 0;
     for (int z0 = 0; z0 < g.zl + 2 && rc == 0; z0 += chunk) {
         const int nz = std::min(chunk, g.zl + 2 - z0);
@@ -754,7 +763,6 @@ static int transfer_populations(lbm_b200* h, double* host, int layout, int field
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(LBM_B200_ECUDA, "population transfer failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(stage);
     return rc;
 }
 
@@ -784,9 +792,10 @@ int lbm_b200_init_equilibrium(lbm_b200_t* h, const double* rho, const double* u)
     const size_t plane_cells = (size_t) (g.xl + 2) * (g.yl + 2);
     int chunk = (int) std::max<size_t>(1, ((size_t) 256 << 20) / (plane_cells * 4 * sizeof(double)));
     chunk = std::min(chunk, g.zl + 2);
-    double *d_rho = nullptr, *d_u = nullptr;
-    CU(cudaMalloc(&d_rho, plane_cells * chunk * sizeof(double)));
-    if (cudaMalloc(&d_u, plane_cells * chunk * 3 * sizeof(double)) != cudaSuccess) { cudaFree(d_rho); cudaGetLastError(); return fail(LBM_B200_ENOMEM, "staging allocation failed"); }
+    DevBuf rho_buf, u_buf;
+    CU(cudaMalloc(&rho_buf.p, plane_cells * chunk * sizeof(double)));
+    CU(cudaMalloc(&u_buf.p, plane_cells * chunk * 3 * sizeof(double)));
+    double *d_rho = rho_buf.as<double>(), *d_u = u_buf.as<double>();
     int rc = 0;
     for (int z0 = 0; z0 < g.zl + 2 && rc == 0; z0 += chunk) {
         const int nz = std::min(chunk, g.zl + 2 - z0);
@@ -803,8 +812,6 @@ int lbm_b200_init_equilibrium(lbm_b200_t* h, const double* rho, const double* u)
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(LBM_B200_ECUDA, "equilibrium initialisation failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(d_rho);
-    cudaFree(d_u);
     if (rc == 0) { h->first = true; h->materialized = true; }
     return rc;
 }
@@ -897,8 +904,9 @@ int lbm_b200_diagnostics(lbm_b200_t* h, double* mass, double* kinetic, double* u
     const Layout& g = h->g;
     dim3 grid((g.xl + 127) / 128, g.yl, g.zl);
     const size_t nblk = (size_t) grid.x * grid.y * grid.z;
-    double* d_part = nullptr;
-    CU(cudaMalloc(&d_part, nblk * 3 * sizeof(double)));
+    DevBuf part_buf;
+    CU(cudaMalloc(&part_buf.p, nblk * 3 * sizeof(double)));
+    double* d_part = part_buf.as<double>();
     dispatch_q(h->Q, [&](auto Qc) {
         diagnostics_kernel<decltype(Qc)::value><<<grid, 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, g, d_part);
         return 0;
@@ -908,7 +916,6 @@ int lbm_b200_diagnostics(lbm_b200_t* h, double* mass, double* kinetic, double* u
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d_part, nblk * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_part);
     if (e != cudaSuccess) return fail(LBM_B200_ECUDA, "diagnostics failed: %s", cudaGetErrorString(e));
     double m = 0.0, k = 0.0, um = 0.0;
     for (size_t b = 0; b < nblk; ++b) { m += part[3 * b]; k += part[3 * b + 1]; um = std::max(um, part[3 * b + 2]); }
@@ -1054,6 +1061,22 @@ int lbm_b200_connect(lbm_b200_t* h, int side, const void* blob)
     h->peer_ipc_base[side] = base;
     unsigned long long* nb_flags = reinterpret_cast<unsigned long long*>((double*) base + 2 * meta[0] * meta[3]);
     return connect_common(h, side, (double*) base, nb_flags, meta[0], meta[1], meta[2], meta[3]);
+}
+
+// Drops the peer mappings (after the caller has synchronised every slab): a slab must not be
+// destroyed while a neighbour can still store into it.
+int lbm_b200_disconnect(lbm_b200_t* h)
+{
+    GUARD(h);
+    CU(cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < 2; ++s) {
+        if (h->peer_ipc_base[s]) cudaIpcCloseMemHandle(h->peer_ipc_base[s]);
+        h->peer_ipc_base[s] = nullptr;
+        h->peer_f[s][0] = h->peer_f[s][1] = nullptr;
+        h->peer_flag[s] = nullptr;
+    }
+    cudaGetLastError();
+    return 0;
 }
 
 int lbm_b200_connect_local(lbm_b200_t* h, int side, lbm_b200_t* nb)

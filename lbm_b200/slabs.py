@@ -176,6 +176,13 @@ class SlabRunner:
             self.dom.halo_pushed()
 
     def close(self):
+        """collective for the p2p transport: nobody frees its slab while a neighbour still maps it"""
+        if self.transport == "p2p":
+            import torch.distributed as dist
+            self.dom.sync()
+            dist.barrier(group=self.group)
+            self.dom.disconnect()
+            dist.barrier(group=self.group)
         self.dom.close()
 
 
@@ -257,5 +264,9 @@ class LocalSlabStack:
         return rho, u
 
     def close(self):
+        for s in self.slabs:
+            s.sync()
+        for s in self.slabs:
+            s.disconnect()
         for s in self.slabs:
             s.close()
