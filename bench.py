@@ -309,19 +309,27 @@ def main():
 
 
 def measure_e2e(torch, dist, capi, run, args, world, cells_per_step):
+    """The same metric through the reference-facing calls with HOST buffers, wall clock, per rank:
+       Domain::setBoundaryCondition...  -> lbm_b200_set_geometry(kind map, handler-id map, table)   [H2D, pinned]
+       K x { stream(); swap(); collide(); } -> lbm_b200_step(K)
+       io::write_vtk_file's read-out      -> lbm_b200_macroscopic(rho, u)                            [D2H, pinned]
+    i.e. what one output interval of src/main.cpp costs when the scenario is (re)applied from the host."""
+    import ctypes as C
     dom = run.dom
     n_int = dom.xl * dom.yl * dom.zl
-    kind = torch.from_numpy(dom.kind()).pin_memory()
-    # the bc-id map is rebuilt from the same boxes; ship it as a second pinned map
+    kind_np, bcid_np, table = capi.paint_boxes(dom.xl, dom.yl, dom.zl, dom.z_first,
+                                               cavity_boxes(dom.xl, dom.yl, dom.zl_global))
+    kind = torch.from_numpy(kind_np).pin_memory()
+    bcid = torch.from_numpy(bcid_np.view("int16")).pin_memory()      # same bits; torch has no uint16 pinning on all builds
+    _, tab = capi._boxes_arrays([(k, v, rho, (0,) * 6) for (k, v, rho) in table])
     rho = torch.empty(n_int, dtype=torch.float64).pin_memory()
     u = torch.empty(3 * n_int, dtype=torch.float64).pin_memory()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    # H2D: geometry (kind map) through the public call; boxes re-applied on top keep the bc ids
-    dom.set_boxes(cavity_boxes(dom.xl, dom.yl, dom.zl_global))
-    run.step(0)
+    capi._check(capi.lib.lbm_b200_set_geometry(dom._h, kind.data_ptr(), bcid.data_ptr(), C.cast(tab, C.c_void_p), len(table)))
+    run.step(0)                       # commits the geometry (scatter + link mask) before the steps
     run.sync()
     t1 = time.perf_counter()
     run.step(args.steps)
@@ -337,13 +345,15 @@ def measure_e2e(torch, dist, capi, run, args, world, cells_per_step):
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    h2d = (kind.numel() * 3) / args.steps          # uint8 kind + uint16 bc-id maps
+    h2d = (kind.numel() + 2 * bcid.numel()) / args.steps
     d2h = (rho.numel() + u.numel()) * 8 / args.steps
     return {"value": round(cells_per_step * args.steps / dt / 1e6, 1), "unit": "MLUPS",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "breakdown_ms": {"geometry_h2d": round(1e3 * (t1 - t0), 1), "steps": round(1e3 * (t2 - t1), 1),
                              "macroscopic_d2h": round(1e3 * (t3 - t2), 1)},
-            "protocol": "per rank: geometry maps H2D + %d steps + density/velocity D2H to pinned host memory, wall clock" % args.steps}
+            "protocol": "per rank: kind + handler-id maps H2D from pinned memory (lbm_b200_set_geometry), %d steps, "
+                        "density/velocity D2H into pinned memory (lbm_b200_macroscopic); wall clock, max over ranks; "
+                        "bytes are totals divided by the %d steps" % (args.steps, args.steps)}
 
 
 if __name__ == "__main__":

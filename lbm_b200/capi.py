@@ -129,6 +129,24 @@ def _boxes_arrays(boxes):
     return ext, tab
 
 
+def paint_boxes(xl, yl, zl_local, z_first, boxes):
+    """Dense kind / bc-id maps (Domain::idx order, local planes 0..zl_local+1 of a slab whose first interior
+    plane is global z_first) and the handler table for a box list -- what Domain::setBoundaryCondition builds
+    on the host (domain.hpp:175-194), last writer wins."""
+    kind = np.zeros((zl_local + 2, yl + 2, xl + 2), dtype=np.uint8)
+    bcid = np.zeros((zl_local + 2, yl + 2, xl + 2), dtype=np.uint16)
+    table = []
+    off = z_first - 1
+    for (k, v, rho, (x0, xE, y0, yE, z0, zE)) in boxes:
+        table.append((k, v, rho))
+        lz0, lz1 = max(z0 - off, 0), min(zE - off, zl_local + 1)
+        if lz0 > lz1:
+            continue
+        kind[lz0:lz1 + 1, y0:yE + 1, x0:xE + 1] = k
+        bcid[lz0:lz1 + 1, y0:yE + 1, x0:xE + 1] = len(table) - 1
+    return kind.reshape(-1), bcid.reshape(-1), table
+
+
 class Domain:
     """Python mirror of lbm::Domain<M> + BGKCollision<M>(tau) backed by one GPU slab.
 

@@ -100,6 +100,8 @@ struct lbm_b200 {
     std::vector<lbm_b200_bc> h_bc;
     bool geom_dirty = true;
     bool geom_unchecked = false;   // maps supplied as arrays, not validated yet
+    uint8_t* stage_kind = nullptr; // dense copies already on the device (set_geometry), consumed by commit
+    uint16_t* stage_bcid = nullptr;
     double* d_rho = nullptr;       // persistent read-out staging
     double* d_u = nullptr;
     bool first = true;         // boundary cells hold host-visible (stored) values
@@ -176,6 +178,45 @@ int fill_weights(lbm_b200* h, int buffer)
     return 0;
 }
 
+// Checks the dense host maps (optionally copying them from caller arrays in the same parallel pass):
+// known kinds, bc ids inside the table and of the same kind, PERIODIC only on the ghost shell.
+int validate_maps(lbm_b200* h, const uint8_t* kind_src, const uint16_t* bcid_src)
+{
+    const Layout& g = h->g;
+    const int nb = (int) h->h_bc.size();
+    const size_t rows = (size_t) (g.zl + 2) * (g.yl + 2);
+    int bad = 0;
+    long long bad_at = -1;
+    #pragma omp parallel for schedule(static)
+    for (long long r = 0; r < (long long) rows; ++r) {
+        const int z = (int) (r / (g.yl + 2)), y = (int) (r % (g.yl + 2));
+        const size_t row = (size_t) r * (g.xl + 2);
+        if (kind_src) memcpy(&h->h_kind[row], kind_src + row, (size_t) g.xl + 2);
+        if (kind_src && bcid_src) memcpy(&h->h_bcid[row], bcid_src + row, ((size_t) g.xl + 2) * sizeof(uint16_t));
+        if (kind_src && !bcid_src) memset(&h->h_bcid[row], 0, ((size_t) g.xl + 2) * sizeof(uint16_t));
+        for (int x = 0; x < g.xl + 2; ++x) {
+            const int k = h->h_kind[row + x];
+            int why = 0;
+            if (k >= K_COUNT) why = 1;
+            else if (k >= K_NOSLIP && k <= K_PRESSURE) {
+                const int id = h->h_bcid[row + x];
+                if (id >= nb) why = 2;
+                else if (h->h_bc[id].kind != k) why = 3;
+            } else if (k == K_PERIODIC && x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1) why = 4;
+            if (why) {
+                #pragma omp critical
+                if (!bad) { bad = why; bad_at = (long long) (row + x); }
+            }
+        }
+    }
+    if (bad) {
+        const long long x = bad_at % (g.xl + 2), y = (bad_at / (g.xl + 2)) % (g.yl + 2), z = bad_at / ((long long) (g.xl + 2) * (g.yl + 2));
+        const char* msg[] = { "", "unknown kind", "bc id outside the table", "kind differs from table[bc id].kind", "PERIODIC is a ghost-shell kind" };
+        return fail(LBM_B200_EINVAL, "cell (%lld,%lld,%lld): %s", x, y, z, msg[bad]);
+    }
+    return 0;
+}
+
 // upload maps, boundary table, link mask, ghost-fluid list
 int commit_geometry(lbm_b200* h)
 {
@@ -198,36 +239,8 @@ int commit_geometry(lbm_b200* h)
         CU(cudaMemcpyAsync(h->d_bc, recs.data(), recs.size() * sizeof(BcRec), cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
-    // validate (only maps that came from the caller as arrays; boxes were checked one by one)
-    const int nb = (int) h->h_bc.size();
     if (h->geom_unchecked) {
-        const size_t rows = (size_t) (g.zl + 2) * (g.yl + 2);
-        int bad = 0;
-        long long bad_at = -1;
-        #pragma omp parallel for schedule(static)
-        for (long long r = 0; r < (long long) rows; ++r) {
-            const int z = (int) (r / (g.yl + 2)), y = (int) (r % (g.yl + 2));
-            const size_t row = (size_t) r * (g.xl + 2);
-            for (int x = 0; x < g.xl + 2; ++x) {
-                const int k = h->h_kind[row + x];
-                int why = 0;
-                if (k >= K_COUNT) why = 1;
-                else if (k >= K_NOSLIP && k <= K_PRESSURE) {
-                    const int id = h->h_bcid[row + x];
-                    if (id >= nb) why = 2;
-                    else if (h->h_bc[id].kind != k) why = 3;
-                } else if (k == K_PERIODIC && x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1) why = 4;
-                if (why) {
-                    #pragma omp critical
-                    if (!bad) { bad = why; bad_at = (long long) (row + x); }
-                }
-            }
-        }
-        if (bad) {
-            const long long x = bad_at % (g.xl + 2), y = (bad_at / (g.xl + 2)) % (g.yl + 2), z = bad_at / ((long long) (g.xl + 2) * (g.yl + 2));
-            const char* msg[] = { "", "unknown kind", "bc id outside the table", "kind differs from table[bc id].kind", "PERIODIC is a ghost-shell kind" };
-            return fail(LBM_B200_EINVAL, "cell (%lld,%lld,%lld): %s", x, y, z, msg[bad]);
-        }
+        TRY(validate_maps(h, nullptr, nullptr));
         h->geom_unchecked = false;
     }
     // ghost-shell cells that kept the fluid handler, and periodic z: only the shell is scanned
@@ -260,13 +273,21 @@ int commit_geometry(lbm_b200* h)
 
     // dense -> padded maps through a device staging copy
     {
-        DevBuf buf8, buf16;
-        CU(cudaMalloc(&buf8.p, n));
-        CU(cudaMalloc(&buf16.p, n * sizeof(uint16_t)));
+        DevBuf buf8, buf16;          // own the staging for the duration of this block either way
+        buf8.p = h->stage_kind;
+        buf16.p = h->stage_bcid;
+        h->stage_kind = nullptr;
+        h->stage_bcid = nullptr;
+        if (!buf8.p || !buf16.p) {   // maps edited on the host (boxes, mask): upload the host copies
+            if (buf8.p) { cudaFree(buf8.p); buf8.p = nullptr; }
+            if (buf16.p) { cudaFree(buf16.p); buf16.p = nullptr; }
+            CU(cudaMalloc(&buf8.p, n));
+            CU(cudaMalloc(&buf16.p, n * sizeof(uint16_t)));
+            CU(cudaMemcpyAsync(buf8.p, h->h_kind.data(), n, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(buf16.p, h->h_bcid.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+        }
         uint8_t* stage8 = buf8.as<uint8_t>();
         uint16_t* stage16 = buf16.as<uint16_t>();
-        CU(cudaMemcpyAsync(stage8, h->h_kind.data(), n, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpyAsync(stage16, h->h_bcid.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemsetAsync(h->d_kind, K_NULL, h->map_elems(), h->stream));
         CU(cudaMemsetAsync(h->d_bcid, 0, h->map_elems() * sizeof(uint16_t), h->stream));
         scatter_map_kernel<uint8_t><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(stage8, h->d_kind, g, 0);
@@ -421,6 +442,14 @@ int materialize(lbm_b200* h)
     CU(cudaGetLastError());
     h->materialized = true;
     return 0;
+}
+
+void drop_staged_maps(lbm_b200* h)
+{
+    if (h->stage_kind) cudaFree(h->stage_kind);
+    if (h->stage_bcid) cudaFree(h->stage_bcid);
+    h->stage_kind = nullptr;
+    h->stage_bcid = nullptr;
 }
 
 // Geometry edits after time steps: first let the boundary cells of the OLD geometry take the values
@@ -595,6 +624,7 @@ int lbm_b200_destroy(lbm_b200_t* h)
     if (h->d_bcid) cudaFree(h->d_bcid);
     if (h->d_bc) cudaFree(h->d_bc);
     if (h->d_ghost) cudaFree(h->d_ghost);
+    drop_staged_maps(h);
     if (h->d_rho) cudaFree(h->d_rho);
     if (h->d_u) cudaFree(h->d_u);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -629,19 +659,33 @@ int lbm_b200_set_stream(lbm_b200_t* h, void* cuda_stream)
 
 int lbm_b200_set_geometry(lbm_b200_t* h, const uint8_t* kind, const uint16_t* bc_id, const lbm_b200_bc* table, int n_table)
 {
-    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    GUARD(h);
     if (!kind) return fail(LBM_B200_EINVAL, "kind map is null");
     if (n_table < 0 || n_table > 65535 || (n_table > 0 && !table)) return fail(LBM_B200_EINVAL, "bad boundary table");
     if (!bc_id && n_table > 1) return fail(LBM_B200_EINVAL, "bc_id map required for a table of %d handlers", n_table);
     TRY(before_geometry_change(h));
     const size_t n = h->ncell();
-    h->h_kind.assign(kind, kind + n);
-    if (bc_id) h->h_bcid.assign(bc_id, bc_id + n);
-    else h->h_bcid.assign(n, 0);
+    // the caller's arrays go to the device straight away (fast when they are pinned) while the host
+    // copies are taken and validated in parallel; commit_geometry() later only scatters them
+    drop_staged_maps(h);
+    CU(cudaMalloc(&h->stage_kind, n));
+    CU(cudaMalloc(&h->stage_bcid, n * sizeof(uint16_t)));
+    CU(cudaMemcpyAsync(h->stage_kind, kind, n, cudaMemcpyHostToDevice, h->stream));
+    if (bc_id) CU(cudaMemcpyAsync(h->stage_bcid, bc_id, n * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    else CU(cudaMemsetAsync(h->stage_bcid, 0, n * sizeof(uint16_t), h->stream));
     h->h_bc.assign(table, table + n_table);
+    h->h_kind.resize(n);
+    h->h_bcid.resize(n);
     h->geom_dirty = true;
-    h->geom_unchecked = true;
     h->materialized = false;
+    const int rc = validate_maps(h, kind, bc_id);
+    CU(cudaStreamSynchronize(h->stream));     // the caller may release its arrays after this call
+    if (rc != 0) {
+        drop_staged_maps(h);
+        h->geom_unchecked = true;             // the next commit reports the same error again
+        return rc;
+    }
+    h->geom_unchecked = false;
     return 0;
 }
 
@@ -650,6 +694,7 @@ int lbm_b200_set_boxes(lbm_b200_t* h, const uint64_t* boxes6, const lbm_b200_bc*
     if (!h) return fail(LBM_B200_EINVAL, "null handle");
     if (n < 0 || (n > 0 && (!boxes6 || !table))) return fail(LBM_B200_EINVAL, "bad box list");
     TRY(before_geometry_change(h));
+    drop_staged_maps(h);   // the host maps become the source of the next commit
     const Layout& g = h->g;
     for (int b = 0; b < n; ++b) {
         const uint64_t* e = boxes6 + 6 * b;
@@ -687,6 +732,7 @@ int lbm_b200_set_fluid_mask(lbm_b200_t* h, const uint8_t* mask)
     if (!mask) return fail(LBM_B200_EINVAL, "mask is null");
     if (h->h_bc.size() >= 65535) return fail(LBM_B200_EINVAL, "more than 65535 boundary handlers");
     TRY(before_geometry_change(h));
+    drop_staged_maps(h);
     const Layout& g = h->g;
     lbm_b200_bc solid{};
     solid.kind = LBM_B200_NOSLIP;
