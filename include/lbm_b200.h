@@ -145,6 +145,11 @@ int lbm_b200_download_populations(lbm_b200_t* h, double* f, int layout, int fiel
  * (collision.hpp:34-51 via Cell::equilibrium, cell.hpp:55-59) */
 int lbm_b200_init_equilibrium(lbm_b200_t* h, const double* rho, const double* u);
 
+/* checkpoint / restart of one slab (not in the reference): the collide field incl. boundary
+ * cells as the reference holds them, plus the step counter.  Geometry is not stored: re-apply it first. */
+int lbm_b200_save_checkpoint(lbm_b200_t* h, const char* path);
+int lbm_b200_load_checkpoint(lbm_b200_t* h, const char* path);
+
 /* --- the hot path: n x { stream(); swap(); collide(); }  (src/main.cpp:50-52) */
 int lbm_b200_step(lbm_b200_t* h, uint64_t n_steps);
 int lbm_b200_sync(lbm_b200_t* h);

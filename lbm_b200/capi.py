@@ -29,6 +29,7 @@ SYMBOLS = [
     "lbm_b200_set_arithmetic", "lbm_b200_set_tau", "lbm_b200_set_stream",
     "lbm_b200_set_geometry", "lbm_b200_set_boxes", "lbm_b200_set_fluid_mask", "lbm_b200_get_kind",
     "lbm_b200_upload_populations", "lbm_b200_download_populations", "lbm_b200_init_equilibrium",
+    "lbm_b200_save_checkpoint", "lbm_b200_load_checkpoint",
     "lbm_b200_step", "lbm_b200_sync", "lbm_b200_elapsed_ms", "lbm_b200_launch_count", "lbm_b200_steps_done",
     "lbm_b200_macroscopic", "lbm_b200_diagnostics",
     "lbm_b200_halo_layout", "lbm_b200_halo_plane", "lbm_b200_dst_buffer",
@@ -72,6 +73,8 @@ lib.lbm_b200_get_kind.argtypes = [_H, C.c_void_p]
 lib.lbm_b200_upload_populations.argtypes = [_H, C.c_void_p, C.c_int, C.c_int]
 lib.lbm_b200_download_populations.argtypes = [_H, C.c_void_p, C.c_int, C.c_int]
 lib.lbm_b200_init_equilibrium.argtypes = [_H, C.c_void_p, C.c_void_p]
+lib.lbm_b200_save_checkpoint.argtypes = [_H, C.c_char_p]
+lib.lbm_b200_load_checkpoint.argtypes = [_H, C.c_char_p]
 lib.lbm_b200_step.argtypes = [_H, C.c_uint64]
 lib.lbm_b200_sync.argtypes = [_H]
 lib.lbm_b200_elapsed_ms.argtypes = [_H, C.POINTER(C.c_double)]
@@ -234,6 +237,12 @@ class Domain:
         u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
         assert rho.size == self.ncell and u.size == 3 * self.ncell
         _check(lib.lbm_b200_init_equilibrium(self._h, rho.ctypes.data, u.ctypes.data))
+
+    def save_checkpoint(self, path):
+        _check(lib.lbm_b200_save_checkpoint(self._h, str(path).encode()))
+
+    def load_checkpoint(self, path):
+        _check(lib.lbm_b200_load_checkpoint(self._h, str(path).encode()))
 
     # -- hot path
     def step(self, n=1):

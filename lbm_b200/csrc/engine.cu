@@ -862,6 +862,84 @@ int lbm_b200_init_equilibrium(lbm_b200_t* h, const double* rho, const double* u)
     return rc;
 }
 
+// ---- checkpoint / restart (absent in the reference) ------------------------------
+// File: 64-byte header {magic "LBMB200\0", version, Q, xl, yl, zl_local, z_first, zl_global, steps, tau}
+// followed by the collide field as Q dense arrays in Domain::idx order (layout LBM_B200_SOA).
+namespace {
+struct CheckpointHeader {
+    char magic[8];
+    int32_t version, Q;
+    int32_t xl, yl, zl_local, z_first, zl_global, pad;
+    uint64_t steps;
+    double tau;
+    uint64_t reserved;
+};
+static_assert(sizeof(CheckpointHeader) == 64, "checkpoint header layout");
+}
+
+int lbm_b200_save_checkpoint(lbm_b200_t* h, const char* path)
+{
+    GUARD(h);
+    if (!path) return fail(LBM_B200_EINVAL, "null path");
+    TRY(materialize(h));
+    const Layout& g = h->g;
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(LBM_B200_EINVAL, "cannot open %s for writing", path);
+    CheckpointHeader hd{};
+    memcpy(hd.magic, "LBMB200", 8);
+    hd.version = 1; hd.Q = h->Q;
+    hd.xl = g.xl; hd.yl = g.yl; hd.zl_local = g.zl; hd.z_first = h->z_first; hd.zl_global = h->zl_global;
+    hd.steps = h->steps; hd.tau = h->tau;
+    int rc = fwrite(&hd, sizeof hd, 1, fp) == 1 ? 0 : fail(LBM_B200_EINVAL, "write to %s failed", path);
+    const size_t n = h->ncell();
+    std::vector<double> buf(n);
+    const size_t rows = (size_t) (g.yl + 2) * (g.zl + 2);
+    for (int q = 0; q < h->Q && rc == 0; ++q) {
+        const double* d = h->f[h->cur] + (size_t) q * g.qstride + X_SHIFT;
+        cudaError_t e = cudaMemcpy2DAsync(buf.data(), (g.xl + 2) * sizeof(double), d, g.P * sizeof(double),
+                                          (g.xl + 2) * sizeof(double), rows, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(LBM_B200_ECUDA, "checkpoint download failed: %s", cudaGetErrorString(e));
+        else if (fwrite(buf.data(), sizeof(double), n, fp) != n) rc = fail(LBM_B200_EINVAL, "write to %s failed", path);
+    }
+    if (fclose(fp) != 0 && rc == 0) rc = fail(LBM_B200_EINVAL, "closing %s failed", path);
+    return rc;
+}
+
+int lbm_b200_load_checkpoint(lbm_b200_t* h, const char* path)
+{
+    GUARD(h);
+    if (!path) return fail(LBM_B200_EINVAL, "null path");
+    const Layout& g = h->g;
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(LBM_B200_EINVAL, "cannot open %s", path);
+    CheckpointHeader hd{};
+    int rc = 0;
+    if (fread(&hd, sizeof hd, 1, fp) != 1 || memcmp(hd.magic, "LBMB200", 8) != 0 || hd.version != 1)
+        rc = fail(LBM_B200_EINVAL, "%s is not a lbm_b200 checkpoint", path);
+    else if (hd.Q != h->Q || hd.xl != g.xl || hd.yl != g.yl || hd.zl_local != g.zl || hd.z_first != h->z_first || hd.zl_global != h->zl_global)
+        rc = fail(LBM_B200_EINVAL, "%s holds D3Q%d %dx%dx%d (slab at %d of %d), this domain is D3Q%d %dx%dx%d (slab at %d of %d)", path,
+                  hd.Q, hd.xl, hd.yl, hd.zl_local, hd.z_first, hd.zl_global, h->Q, g.xl, g.yl, g.zl, h->z_first, h->zl_global);
+    const size_t n = h->ncell();
+    std::vector<double> buf(rc == 0 ? n : 0);
+    const size_t rows = (size_t) (g.yl + 2) * (g.zl + 2);
+    for (int q = 0; q < h->Q && rc == 0; ++q) {
+        if (fread(buf.data(), sizeof(double), n, fp) != n) { rc = fail(LBM_B200_EINVAL, "%s is truncated", path); break; }
+        double* d = h->f[h->cur] + (size_t) q * g.qstride + X_SHIFT;
+        cudaError_t e = cudaMemcpy2DAsync(d, g.P * sizeof(double), buf.data(), (g.xl + 2) * sizeof(double),
+                                          (g.xl + 2) * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(LBM_B200_ECUDA, "checkpoint upload failed: %s", cudaGetErrorString(e));
+    }
+    fclose(fp);
+    if (rc == 0) {
+        h->steps = hd.steps;
+        h->first = true;          // boundary cells hold the stored (materialised) values again
+        h->materialized = true;
+    }
+    return rc;
+}
+
 // ---- hot path ---------------------------------------------------------------
 int lbm_b200_step(lbm_b200_t* h, uint64_t n_steps)
 {

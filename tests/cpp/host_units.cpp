@@ -145,6 +145,33 @@ static void check_xml(const char* tmpdir)
         CHECK(xml::load_file(s, doc) && doc.child("scenario") && doc.child("scenario")->child("domain"));
 }
 
+static void check_scenario_errors(const char* tmpdir)
+{
+    using M = lbm::model::d3q19;
+    const std::string cfgfile = std::string(tmpdir) + "/t.cfg";
+    const char* argv[] = { "lbm", cfgfile.c_str() };
+    lbm::io::Config cfg(2, const_cast<char**>(argv));
+    lbm::BGKCollision<M> bgk(0.6);
+    auto expect = [&](const std::string& xml_text, const std::string& needle) {
+        const std::string file = std::string(tmpdir) + "/bad.xml";
+        { std::ofstream f(file); f << xml_text; }
+        std::string what;
+        try { lbm::io::parse_scenario_file<M>(file, cfg, bgk); } catch (const std::logic_error& e) { what = e.what(); }
+        if (what.find(needle) == std::string::npos) { std::printf("FAILED: expected \"%s\" in \"%s\"\n", needle.c_str(), what.c_str()); ++failures; }
+    };
+    // messages of io/scenario.h:138-175
+    expect("<nonsense", "could not be read properly!");
+    expect("<other name=\"x\"/>", "Scenario node missing!");
+    expect("<scenario><domain xl=\"2\" yl=\"2\" zl=\"2\"/></scenario>", "Scenario name is missing!");
+    expect("<scenario name=\"s\"></scenario>", "Domain node is missing!");
+    expect("<scenario name=\"s\"><domain xl=\"2\" yl=\"2\"/></scenario>", "Neither vtk-file nor xl/yl/zl attribute provided to domain node!");
+    expect("<scenario name=\"s\"><domain vtk-file=\"/nonexistent.vtk\"/></scenario>", "does not exist or does not seem to be a valid structured grids file!");
+    std::string what;
+    try { lbm::io::parse_scenario_file<M>(std::string(tmpdir) + "/absent.xml", cfg, bgk); } catch (const std::logic_error& e) { what = e.what(); }
+    CHECK(what.find("could not be read properly!") != std::string::npos);
+    CHECK(cfg.output_filename() == "s");      // set from the scenario name before the domain is built (io/scenario.h:149)
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 2) { std::printf("usage: host_units <tmpdir>\n"); return 2; }
@@ -154,6 +181,7 @@ int main(int argc, char** argv)
     CHECK(lbm::C_S * lbm::C_S == 0.33333333333376547);
     check_config(argv[1]);
     check_xml(argv[1]);
+    check_scenario_errors(argv[1]);
     if (lbm_b200_device_count() == 0) {   // without a GPU a Domain cannot exist: loud failure, no fallback
         bool threw = false;
         lbm::BGKCollision<lbm::model::d3q19> bgk(0.6);

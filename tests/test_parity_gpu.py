@@ -209,3 +209,27 @@ def test_geometry_change_between_steps():
     cpu = O.oracle().run(Q, n, n, n, TAU, base + block, 6, f_init=mid)
     fluid = cpu["kind"] == O.FLUID
     assert_bitwise("after geometry change", got[fluid], cpu["f"][fluid])
+
+
+def test_checkpoint_restart_continues_bit_exactly(tmp_path):
+    from lbm_b200 import capi
+    Q, case = 27, cases.channel(18, 7, 6, block=(5, 8, 2, 4, 0, 3))
+    ck = tmp_path / "state.lbm"
+    with capi.Domain(Q, case["xl"], case["yl"], case["zl"], TAU, exact=True) as a:
+        a.set_boxes(case["boxes"])
+        a.step(13)
+        a.save_checkpoint(ck)
+        a.step(11)
+        end = a.download()
+    with capi.Domain(Q, case["xl"], case["yl"], case["zl"], TAU, exact=True) as b:
+        b.set_boxes(case["boxes"])
+        b.load_checkpoint(ck)
+        assert b.steps_done() == 13
+        b.step(11)
+        assert_bitwise("restart from checkpoint", b.download(), end)
+    assert_bitwise("vs oracle", end, run_cpu(Q, case, 24)["f"])
+    with capi.Domain(19, case["xl"], case["yl"], case["zl"], TAU) as c:
+        with pytest.raises(capi.LbmError):
+            c.load_checkpoint(ck)                      # wrong lattice
+        with pytest.raises(capi.LbmError):
+            c.load_checkpoint(tmp_path / "missing")
