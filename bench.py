@@ -190,8 +190,15 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    if not os.path.exists(os.path.join(ROOT, "lbm_b200", "liblbm_b200.so")) and local_rank == 0:
+        import __graft_entry__            # a fresh checkout: compile the CUDA library (nvcc, sm_100a) first
+        __graft_entry__.build()
     import torch
     import torch.distributed as dist
+    for _ in range(600):                  # other ranks wait for rank 0's build
+        if os.path.exists(os.path.join(ROOT, "lbm_b200", "liblbm_b200.so")):
+            break
+        time.sleep(1.0)
     from lbm_b200 import capi
     from lbm_b200.slabs import SlabRunner
 

@@ -19,3 +19,13 @@ def built():
     import __graft_entry__ as g
     g.build()
     return True
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _library_present():
+    """GPU and CPU tests alike need the in-tree shared libraries; build them once if a fresh checkout lacks them."""
+    lib = os.path.join(ROOT, "lbm_b200", "liblbm_b200.so")
+    orc = os.path.join(ROOT, "oracle", "liblbm_oracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        import __graft_entry__ as g
+        g.build()
