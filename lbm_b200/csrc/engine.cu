@@ -107,6 +107,7 @@ struct lbm_b200 {
     bool first = true;         // boundary cells hold host-visible (stored) values
     bool materialized = true;  // boundary cells of f[cur] hold the reference's values
     int wrap_z = 0;
+    bool ring_lo = false, ring_hi = false;   // periodic z must be closed by a slab ring on that side
 
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -264,8 +265,13 @@ int commit_geometry(lbm_b200* h)
             }
         }
     }
-    if (periodic_z && (h->z_first != 1 || g.zl != h->zl_global))
-        periodic_z = false;   // closed by the slab ring exchange instead
+    h->ring_lo = h->ring_hi = false;
+    if (periodic_z && (h->z_first != 1 || g.zl != h->zl_global)) {
+        // closed by a ring of slabs instead: the first and the last slab must be each other's neighbours
+        h->ring_lo = h->z_first == 1;
+        h->ring_hi = h->z_first + g.zl - 1 == h->zl_global;
+        periodic_z = false;
+    }
     h->wrap_z = periodic_z ? 1 : 0;
     if (!ghost.empty() && g.zl != h->zl_global)
         return fail(LBM_B200_EINVAL, "%zu ghost-shell cells carry the fluid handler; on a multi-slab domain the "
@@ -946,6 +952,9 @@ int lbm_b200_step(lbm_b200_t* h, uint64_t n_steps)
     GUARD(h);
     if (h->edges_done) return fail(LBM_B200_ESTATE, "a split-phase step is in flight");
     TRY(commit_geometry(h));
+    if ((h->ring_lo && !h->peer_f[LBM_B200_DOWN][0]) || (h->ring_hi && !h->peer_f[LBM_B200_UP][0]))
+        return fail(LBM_B200_ESTATE, "periodic z on a multi-slab domain needs the first and last slab connected as a ring "
+                    "(lbm_b200_connect / lbm_b200_connect_local on that side)");
     CU(cudaEventRecord(h->ev_a, h->stream));
     for (uint64_t s = 0; s < n_steps; ++s) {
         if (has_peers(h) && h->g.zl >= 3) {

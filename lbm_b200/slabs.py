@@ -196,6 +196,7 @@ class LocalSlabStack:
         import numpy as np
         self.np = np
         self.Q, self.xl, self.yl, self.zl = Q, xl, yl, zl
+        self.periodic_z = periodic_z and n_slabs > 1
         self.ranges = partition(zl, n_slabs)
         devices = devices or [0] * n_slabs
         self.slabs = [capi.Domain(Q, xl, yl, zl, tau, device=devices[r], z_first=zf, zl_local=nz, exact=exact)
@@ -214,10 +215,14 @@ class LocalSlabStack:
                 self.slabs[r].connect_local(DOWN, self.slabs[down])
 
     def upload(self, f):
-        """f: [(xl+2)(yl+2)(zl+2), Q] global AoS; every slab gets its planes plus both ghost planes"""
+        """f: [(xl+2)(yl+2)(zl+2), Q] global AoS; every slab gets its planes plus both ghost planes
+        (for a periodic ring the two global ghost planes are first filled with their wrapped images)"""
         np = self.np
         plane = (self.xl + 2) * (self.yl + 2)
-        f = np.asarray(f).reshape(self.zl + 2, plane, self.Q)
+        f = np.array(f, dtype=np.float64).reshape(self.zl + 2, plane, self.Q)
+        if self.periodic_z:
+            f[0] = f[self.zl]
+            f[self.zl + 1] = f[1]
         for (zf, nz), s in zip(self.ranges, self.slabs):
             s.upload(np.ascontiguousarray(f[zf - 1:zf + nz + 1]))
 
