@@ -20,6 +20,10 @@
  *     included, local to the handle (a slab has zl_local+2 planes).
  *   - there is NO CPU fallback: without a CUDA device every compute entry
  *     point fails with LBM_B200_ECUDA.
+ *   - a handle is driven by one host thread at a time (like the reference's
+ *     Domain); different handles may be used from different threads.  Calls
+ *     that enqueue work (step) return before the GPU has finished; calls that
+ *     return data synchronise.
  */
 #ifndef LBM_B200_H
 #define LBM_B200_H

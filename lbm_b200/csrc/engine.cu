@@ -19,6 +19,12 @@
 
 using namespace lbmb200;
 
+// the device code's kind numbering is the ABI's
+static_assert(K_FLUID == LBM_B200_FLUID && K_NOSLIP == LBM_B200_NOSLIP && K_MOVINGWALL == LBM_B200_MOVINGWALL
+              && K_FREESLIP == LBM_B200_FREESLIP && K_OUTFLOW == LBM_B200_OUTFLOW && K_INFLOW == LBM_B200_INFLOW
+              && K_PRESSURE == LBM_B200_PRESSURE && K_NULL == LBM_B200_NULL && K_PARALLEL == LBM_B200_PARALLEL
+              && K_PERIODIC == LBM_B200_PERIODIC, "kind enums of kernels.cuh and lbm_b200.h must agree");
+
 namespace {
 
 thread_local std::string g_error;
@@ -123,6 +129,8 @@ struct lbm_b200 {
     long long peer_qstride[2] = { 0, 0 };
     long long peer_off[2] = { 0, 0 };
     void* peer_ipc_base[2] = { nullptr, nullptr };
+    cudaIpcMemHandle_t peer_ipc_handle[2] = {};
+    bool peer_ipc_shared = false;                   // both sides map the same exporter (ring of two)
     unsigned long long* d_flags = nullptr;          // [side]: sweeps completed by the neighbour on that side
     unsigned long long* peer_flag[2] = { nullptr, nullptr };   // the neighbour's counter for us
     unsigned long long halo_epoch = 0;              // sweeps completed since the peers were connected
@@ -619,6 +627,7 @@ int lbm_b200_destroy(lbm_b200_t* h)
         }
         cudaFree(h->d_trace);
     }
+    if (h->peer_ipc_shared) h->peer_ipc_base[1] = nullptr;
     for (int s = 0; s < 2; ++s) {
         if (h->peer_ipc_base[s]) cudaIpcCloseMemHandle(h->peer_ipc_base[s]);
     }
@@ -1190,8 +1199,15 @@ int lbm_b200_connect(lbm_b200_t* h, int side, const void* blob)
     long long meta[4];
     memcpy(meta, p + 64, sizeof meta);
     void* base = nullptr;
-    CU(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+    const int other = 1 - side;
+    if (h->peer_ipc_base[other] && memcmp(&h->peer_ipc_handle[other], &mh, sizeof mh) == 0) {
+        base = h->peer_ipc_base[other];          // ring of two: the same neighbour on both sides, map it once
+        h->peer_ipc_shared = true;
+    } else {
+        CU(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+    }
     h->peer_ipc_base[side] = base;
+    h->peer_ipc_handle[side] = mh;
     unsigned long long* nb_flags = reinterpret_cast<unsigned long long*>((double*) base + 2 * meta[0] * meta[3]);
     return connect_common(h, side, (double*) base, nb_flags, meta[0], meta[1], meta[2], meta[3]);
 }
@@ -1202,6 +1218,8 @@ int lbm_b200_disconnect(lbm_b200_t* h)
 {
     GUARD(h);
     CU(cudaStreamSynchronize(h->stream));
+    if (h->peer_ipc_shared) h->peer_ipc_base[1] = nullptr;   // mapped once
+    h->peer_ipc_shared = false;
     for (int s = 0; s < 2; ++s) {
         if (h->peer_ipc_base[s]) cudaIpcCloseMemHandle(h->peer_ipc_base[s]);
         h->peer_ipc_base[s] = nullptr;
