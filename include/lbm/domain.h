@@ -84,10 +84,18 @@ class Domain
     std::vector<std::uint16_t> null_original;
     std::uint64_t null_tagged_at { 0 };
 
-    // host mirror behind cell()
-    mutable Lattice_field<lattice_model> mirror;
-    mutable bool mirror_valid { false };
-    mutable bool mirror_dirty { false };
+    // Host mirror behind cell(): one x-y plane at a time, downloaded on first access after a step
+    // and uploaded before the next step if a mutable reference into it was handed out.  Touching
+    // a few cells of a 512^3 lattice therefore moves a few 42 MB planes, not the 20 GB lattice.
+    // Plane storage is kept across steps, so references stay valid (and are refreshed when the
+    // plane is fetched again), like references into the reference's Cell vectors.
+    struct PlaneMirror {
+        Lattice_field<lattice_model> cells;
+        bool valid { false };
+        bool dirty { false };
+    };
+    mutable std::vector<PlaneMirror> planes;
+    mutable bool readback_ready { false };   // edge planes pushed across slab cuts for this time level
 
     bool streamed { false }, swapped { false };
     std::uint64_t steps_done { 0 };
@@ -143,59 +151,77 @@ class Domain
         for (auto& s : slabs) device::check(lbm_b200_halo_pushed(s.handle), "lbm_b200_halo_pushed");
     }
 
-    // mirror <-> device
-    void pull_mirror() const
+    // slab that owns global plane z (the two physical ghost planes belong to the first / last slab)
+    std::size_t owner_of(std::size_t z) const
     {
-        if (mirror_valid) return;
-        auto* self = const_cast<Domain*>(this);
-        self->push_geometry();
-        prepare_readback();
-        constexpr std::size_t Q = lattice_model::Q;
-        if (mirror.empty()) mirror.assign(all_cells(), Cell<lattice_model>(collision));
-        std::vector<double> buf;
-        for (std::size_t si = 0; si < slabs.size(); ++si) {
-            const auto& s = slabs[si];
-            const std::size_t local = plane_cells() * (s.zl_local + 2);
-            buf.resize(local * Q);
-            device::check(lbm_b200_download_populations(s.handle, buf.data(), LBM_B200_AOS, LBM_B200_COLLIDE_FIELD),
-                    "lbm_b200_download_populations");
-            // own planes, plus the physical ghost planes at the two ends of the stack
-            const std::size_t p0 = si == 0 ? 0 : 1;
-            const std::size_t p1 = si + 1 == slabs.size() ? s.zl_local + 1 : s.zl_local;
-            for (std::size_t p = p0; p <= p1; ++p)
-                for (std::size_t c = 0; c < plane_cells(); ++c) {
-                    Cell<lattice_model>& dst = mirror[(s.z_first - 1 + p) * plane_cells() + c];
-                    std::memcpy(dst.data(), buf.data() + (p * plane_cells() + c) * Q, Q * sizeof(double));
-                }
-        }
-        for (std::size_t i = 0; i < mirror.size(); ++i) mirror[i].set_collision_handler(handlers[reported_id(i)]);
-        mirror_valid = true;
-        mirror_dirty = false;
+        for (std::size_t i = 0; i < slabs.size(); ++i)
+            if (z >= slabs[i].z_first && z < slabs[i].z_first + slabs[i].zl_local) return i;
+        return z == 0 ? 0 : slabs.size() - 1;
+    }
+    bool any_dirty() const
+    {
+        for (const auto& pm : planes)
+            if (pm.dirty) return true;
+        return false;
     }
 
+    // mirror <- device
+    void fetch_plane(std::size_t z) const
+    {
+        PlaneMirror& pm = planes[z];
+        if (pm.valid) return;
+        auto* self = const_cast<Domain*>(this);
+        self->push_geometry();
+        if (!readback_ready) {
+            prepare_readback();
+            readback_ready = true;
+        }
+        constexpr std::size_t Q = lattice_model::Q;
+        if (pm.cells.empty()) pm.cells.assign(plane_cells(), Cell<lattice_model>(collision));
+        const Slab& s = slabs[owner_of(z)];
+        std::vector<double> buf(plane_cells() * Q);
+        device::check(lbm_b200_download_planes(s.handle, buf.data(), LBM_B200_COLLIDE_FIELD, z - (s.z_first - 1), 1),
+                "lbm_b200_download_planes");
+        for (std::size_t c = 0; c < plane_cells(); ++c) {
+            std::memcpy(pm.cells[c].data(), buf.data() + c * Q, Q * sizeof(double));
+            pm.cells[c].set_collision_handler(handlers[reported_id(z * plane_cells() + c)]);
+        }
+        pm.valid = true;
+        pm.dirty = false;
+    }
+
+    // mirror -> device: planes that may have been written, to every slab that stores them
     void push_mirror()
     {
-        if (!mirror_dirty) return;
         constexpr std::size_t Q = lattice_model::Q;
-        // handlers may have been changed through Cell::set_collision_handler
-        for (std::size_t i = 0; i < mirror.size(); ++i) {
-            const auto* h = mirror[i].get_collision_handler();
-            if (h != handlers[reported_id(i)]) {
-                handler_id[i] = intern(h);
-                untag(i);
-                geometry_dirty = true;
-            }
-        }
         std::vector<double> buf;
-        for (auto& s : slabs) {
-            const std::size_t local = plane_cells() * (s.zl_local + 2);
-            buf.resize(local * Q);
-            const std::size_t off = (s.z_first - 1) * plane_cells();
-            for (std::size_t c = 0; c < local; ++c) std::memcpy(buf.data() + c * Q, mirror[off + c].data(), Q * sizeof(double));
-            device::check(lbm_b200_upload_populations(s.handle, buf.data(), LBM_B200_AOS, LBM_B200_COLLIDE_FIELD),
-                    "lbm_b200_upload_populations");
+        for (std::size_t z = 0; z < planes.size(); ++z) {
+            PlaneMirror& pm = planes[z];
+            if (!pm.dirty) continue;
+            // handlers may have been changed through Cell::set_collision_handler
+            for (std::size_t c = 0; c < plane_cells(); ++c) {
+                const std::size_t i = z * plane_cells() + c;
+                const auto* h = pm.cells[c].get_collision_handler();
+                if (h != handlers[reported_id(i)]) {
+                    handler_id[i] = intern(h);
+                    untag(i);
+                    geometry_dirty = true;
+                }
+            }
+            buf.resize(plane_cells() * Q);
+            for (std::size_t c = 0; c < plane_cells(); ++c) std::memcpy(buf.data() + c * Q, pm.cells[c].data(), Q * sizeof(double));
+            for (auto& s : slabs)
+                if (z + 1 >= s.z_first && z <= s.z_first + s.zl_local)   // own plane or one of its two ghost planes
+                    device::check(lbm_b200_upload_planes(s.handle, buf.data(), LBM_B200_COLLIDE_FIELD, z - (s.z_first - 1), 1),
+                            "lbm_b200_upload_planes");
+            pm.dirty = false;
         }
-        mirror_dirty = false;
+    }
+
+    void invalidate_mirror()
+    {
+        for (auto& pm : planes) pm.valid = false;
+        readback_ready = false;
     }
 
     void require_idle(const char* what) const
@@ -218,6 +244,7 @@ public:
                     "collision-model == bgk as well, io/configuration.h:126-128)");
         handlers.push_back(collision);
         handler_id.assign(all_cells(), 0);
+        planes.resize(zl + 2);
         int n = device::gpus();
         if (std::size_t(n) > zl) n = int(zl);
         const int visible = lbm_b200_device_count();
@@ -272,21 +299,22 @@ public:
     auto cell(int x, int y, int z) const -> const Cell<lattice_model>&
     {
         require_idle("Domain::cell()");
-        pull_mirror();
-        return mirror[idx(x, y, z)];
+        fetch_plane(std::size_t(z));
+        return planes[std::size_t(z)].cells[std::size_t(x) + (xl + 2) * std::size_t(y)];
     }
     auto cell(int x, int y, int z) -> Cell<lattice_model>&
     {
         require_idle("Domain::cell()");
-        pull_mirror();
-        mirror_dirty = true;   // a mutable reference escapes: assume it is written
-        return mirror[idx(x, y, z)];
+        fetch_plane(std::size_t(z));
+        planes[std::size_t(z)].dirty = true;   // a mutable reference escapes: assume it is written
+        return planes[std::size_t(z)].cells[std::size_t(x) + (xl + 2) * std::size_t(y)];
     }
 
     // handler of a cell without touching the population mirror
     auto handler(int x, int y, int z) const -> const Collision<lattice_model>*
     {
-        if (mirror_valid && mirror_dirty) return mirror[idx(x, y, z)].get_collision_handler();
+        const PlaneMirror& pm = planes[std::size_t(z)];
+        if (pm.valid && pm.dirty) return pm.cells[std::size_t(x) + (xl + 2) * std::size_t(y)].get_collision_handler();
         return handlers[reported_id(std::size_t(idx(x, y, z)))];
     }
 
@@ -296,7 +324,7 @@ public:
     auto set_nonfluid_cells_nullcollide() -> void
     {
         require_idle("set_nonfluid_cells_nullcollide()");
-        if (mirror_valid && mirror_dirty) push_mirror();
+        push_mirror();
         static NullCollision<lattice_model> null_collision;
         std::vector<std::size_t> lonely;
         for (int z = 1; z < int(zl) + 1; ++z)
@@ -320,8 +348,10 @@ public:
             if (handler_id[i] != id) null_original[i] = handler_id[i];
             handler_id[i] = id;
         }
-        if (mirror_valid)
-            for (auto i : lonely) mirror[i].set_collision_handler(&null_collision);
+        for (auto i : lonely) {
+            PlaneMirror& pm = planes[i / plane_cells()];
+            if (pm.valid) pm.cells[i % plane_cells()].set_collision_handler(&null_collision);
+        }
         geometry_dirty = true;
     }
 
@@ -332,7 +362,7 @@ public:
         require_idle("setBoundaryCondition()");
         if (!(xE >= x0 && yE >= y0 && zE >= z0) || !(xE < xl + 2 && yE < yl + 2 && zE < zl + 2))
             throw std::out_of_range("setBoundaryCondition: extent outside the domain (the reference asserts this, domain.hpp:180-181)");
-        if (mirror_valid && mirror_dirty) push_mirror();
+        push_mirror();
         const std::uint16_t id = intern(&condition);
         for (auto z = z0; z <= zE; ++z)
             for (auto y = y0; y <= yE; ++y)
@@ -340,10 +370,12 @@ public:
                     handler_id[std::size_t(idx(int(x), int(y), int(z)))] = id;
                     untag(std::size_t(idx(int(x), int(y), int(z))));
                 }
-        if (mirror_valid)
-            for (auto z = z0; z <= zE; ++z)
-                for (auto y = y0; y <= yE; ++y)
-                    for (auto x = x0; x <= xE; ++x) mirror[std::size_t(idx(int(x), int(y), int(z)))].set_collision_handler(&condition);
+        for (auto z = z0; z <= zE; ++z) {
+            PlaneMirror& pm = planes[z];
+            if (!pm.valid) continue;
+            for (auto y = y0; y <= yE; ++y)
+                for (auto x = x0; x <= xE; ++x) pm.cells[x + (xl + 2) * y].set_collision_handler(&condition);
+        }
         geometry_dirty = true;
     }
 
@@ -383,7 +415,7 @@ public:
                 for (auto& s : slabs) device::check(lbm_b200_step(s.handle, 1), "lbm_b200_step");
         }
         steps_done += n;
-        mirror_valid = false;
+        if (n > 0) invalidate_mirror();
     }
     auto synchronize() const -> void
     {
@@ -397,7 +429,10 @@ public:
         auto* self = const_cast<Domain*>(this);
         self->push_mirror();
         self->push_geometry();
-        prepare_readback();
+        if (!readback_ready) {
+            prepare_readback();
+            readback_ready = true;
+        }
         for (auto& s : slabs) {
             const std::size_t off = (s.z_first - 1) * xl * yl;
             device::check(lbm_b200_macroscopic(s.handle, rho ? rho + off : nullptr, u ? u + 3 * off : nullptr),

@@ -144,6 +144,10 @@ int lbm_b200_get_kind(lbm_b200_t* h, uint8_t* kind);
 /* --- state ------------------------------------------------------------------ */
 int lbm_b200_upload_populations(lbm_b200_t* h, const double* f, int layout, int field);
 int lbm_b200_download_populations(lbm_b200_t* h, double* f, int layout, int field);
+/* the same for the local x-y planes [z_begin, z_begin+z_count) only, AoS layout: what Domain::cell() uses
+ * when a few cells of a large lattice are read or written */
+int lbm_b200_upload_planes(lbm_b200_t* h, const double* f, int field, uint64_t z_begin, uint64_t z_count);
+int lbm_b200_download_planes(lbm_b200_t* h, double* f, int field, uint64_t z_begin, uint64_t z_count);
 /* f = feq(rho,u) per local cell from host arrays rho[ncell], u[ncell*3] (idx
  * order), evaluated on the device with compute_feq's association
  * (collision.hpp:34-51 via Cell::equilibrium, cell.hpp:55-59) */

@@ -29,7 +29,7 @@ SYMBOLS = [
     "lbm_b200_set_arithmetic", "lbm_b200_set_tau", "lbm_b200_set_stream",
     "lbm_b200_set_geometry", "lbm_b200_set_boxes", "lbm_b200_set_fluid_mask", "lbm_b200_get_kind",
     "lbm_b200_upload_populations", "lbm_b200_download_populations", "lbm_b200_init_equilibrium",
-    "lbm_b200_save_checkpoint", "lbm_b200_load_checkpoint",
+    "lbm_b200_save_checkpoint", "lbm_b200_load_checkpoint", "lbm_b200_upload_planes", "lbm_b200_download_planes",
     "lbm_b200_step", "lbm_b200_sync", "lbm_b200_elapsed_ms", "lbm_b200_launch_count", "lbm_b200_steps_done",
     "lbm_b200_macroscopic", "lbm_b200_diagnostics",
     "lbm_b200_halo_layout", "lbm_b200_halo_plane", "lbm_b200_dst_buffer",
@@ -73,6 +73,8 @@ lib.lbm_b200_get_kind.argtypes = [_H, C.c_void_p]
 lib.lbm_b200_upload_populations.argtypes = [_H, C.c_void_p, C.c_int, C.c_int]
 lib.lbm_b200_download_populations.argtypes = [_H, C.c_void_p, C.c_int, C.c_int]
 lib.lbm_b200_init_equilibrium.argtypes = [_H, C.c_void_p, C.c_void_p]
+lib.lbm_b200_upload_planes.argtypes = [_H, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
+lib.lbm_b200_download_planes.argtypes = [_H, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
 lib.lbm_b200_save_checkpoint.argtypes = [_H, C.c_char_p]
 lib.lbm_b200_load_checkpoint.argtypes = [_H, C.c_char_p]
 lib.lbm_b200_step.argtypes = [_H, C.c_uint64]
@@ -237,6 +239,16 @@ class Domain:
         u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
         assert rho.size == self.ncell and u.size == 3 * self.ncell
         _check(lib.lbm_b200_init_equilibrium(self._h, rho.ctypes.data, u.ctypes.data))
+
+    def download_planes(self, z_begin, z_count, field=COLLIDE_FIELD):
+        f = np.empty((z_count * (self.yl + 2) * (self.xl + 2), self.Q))
+        _check(lib.lbm_b200_download_planes(self._h, f.ctypes.data, field, z_begin, z_count))
+        return f
+
+    def upload_planes(self, f, z_begin, z_count, field=COLLIDE_FIELD):
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        assert f.size == z_count * (self.yl + 2) * (self.xl + 2) * self.Q
+        _check(lib.lbm_b200_upload_planes(self._h, f.ctypes.data, field, z_begin, z_count))
 
     def save_checkpoint(self, path):
         _check(lib.lbm_b200_save_checkpoint(self._h, str(path).encode()))

@@ -777,14 +777,17 @@ int lbm_b200_get_kind(lbm_b200_t* h, uint8_t* kind)
 }
 
 // ---- state ------------------------------------------------------------------
-static int transfer_populations(lbm_b200* h, double* host, int layout, int field, bool upload)
+static int transfer_populations(lbm_b200* h, double* host, int layout, int field, bool upload, int z_begin = 0, int z_count = -1)
 {
     if (!host) return fail(LBM_B200_EINVAL, "population array is null");
     if (field != LBM_B200_COLLIDE_FIELD && field != LBM_B200_STREAM_FIELD) return fail(LBM_B200_EINVAL, "unknown field %d", field);
     const Layout& g = h->g;
     double* dev = h->f[field == LBM_B200_COLLIDE_FIELD ? h->cur : 1 - h->cur];
     const int Q = h->Q;
+    if (z_count < 0) z_count = g.zl + 2 - z_begin;
+    if (z_begin < 0 || z_count < 0 || z_begin + z_count > g.zl + 2) return fail(LBM_B200_EINVAL, "plane range outside the slab");
     if (layout == LBM_B200_SOA) {
+        if (z_begin != 0 || z_count != g.zl + 2) return fail(LBM_B200_EINVAL, "plane ranges use the AoS layout");
         const size_t n = h->ncell();
         for (int q = 0; q < Q; ++q) {
             double* d = dev + (size_t) q * g.qstride + X_SHIFT;
@@ -800,14 +803,14 @@ static int transfer_populations(lbm_b200* h, double* host, int layout, int field
     // chunks of z planes through a device staging buffer of at most ~256 MB
     const size_t plane_vals = (size_t) (g.xl + 2) * (g.yl + 2) * Q;
     int chunk = (int) std::max<size_t>(1, ((size_t) 256 << 20) / (plane_vals * sizeof(double)));
-    chunk = std::min(chunk, g.zl + 2);
+    chunk = std::min(chunk, std::max(1, z_count));
     DevBuf stage_buf;
     CU(cudaMalloc(&stage_buf.p, plane_vals * chunk * sizeof(double)));
     double* stage = stage_buf.as<double>();
     int rc = 0;
-    for (int z0 = 0; z0 < g.zl + 2 && rc == 0; z0 += chunk) {
-        const int nz = std::min(chunk, g.zl + 2 - z0);
-        double* hp = host + plane_vals * z0;
+    for (int z0 = z_begin; z0 < z_begin + z_count && rc == 0; z0 += chunk) {
+        const int nz = std::min(chunk, z_begin + z_count - z0);
+        double* hp = host + plane_vals * (z0 - z_begin);
         cudaError_t e = cudaSuccess;
         if (upload) e = cudaMemcpyAsync(stage, hp, plane_vals * nz * sizeof(double), cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) {
@@ -836,6 +839,26 @@ int lbm_b200_upload_populations(lbm_b200_t* h, const double* f, int layout, int 
         h->materialized = true;
     }
     return 0;
+}
+
+// x-y planes [z_begin, z_begin + z_count) of the slab only (AoS): what Domain::cell() needs when a few
+// cells of a large lattice are touched
+int lbm_b200_upload_planes(lbm_b200_t* h, const double* f, int field, uint64_t z_begin, uint64_t z_count)
+{
+    GUARD(h);
+    if (field == LBM_B200_COLLIDE_FIELD) TRY(materialize(h));   // the other planes' boundary cells must be current
+    TRY(transfer_populations(h, const_cast<double*>(f), LBM_B200_AOS, field, true, (int) z_begin, (int) z_count));
+    if (field == LBM_B200_COLLIDE_FIELD) {
+        h->first = true;
+        h->materialized = true;
+    }
+    return 0;
+}
+int lbm_b200_download_planes(lbm_b200_t* h, double* f, int field, uint64_t z_begin, uint64_t z_count)
+{
+    GUARD(h);
+    if (field == LBM_B200_COLLIDE_FIELD) TRY(materialize(h));
+    return transfer_populations(h, f, LBM_B200_AOS, field, false, (int) z_begin, (int) z_count);
 }
 
 int lbm_b200_download_populations(lbm_b200_t* h, double* f, int layout, int field)
