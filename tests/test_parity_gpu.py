@@ -233,3 +233,23 @@ def test_checkpoint_restart_continues_bit_exactly(tmp_path):
             c.load_checkpoint(ck)                      # wrong lattice
         with pytest.raises(capi.LbmError):
             c.load_checkpoint(tmp_path / "missing")
+
+
+@pytest.mark.parametrize("xml,Q,steps", [("step_small.xml", 19, 40), ("shear_small.xml", 27, 60), ("shear_small.xml", 15, 60),
+                                         ("cavity64.xml", 19, 30)])
+def test_shipped_scenario_files_gpu_vs_oracle(xml, Q, steps):
+    """the same scenario XML feeds both sides: GPU through lbm_b200.scenario, oracle through its box list"""
+    import os
+    from lbm_b200 import scenario
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scenarios", xml)
+    d, sc = scenario.domain_from_scenario(path, Q, TAU, exact=True)
+    try:
+        d.step(steps)
+        f = d.download()
+        rho, u = d.macroscopic()
+    finally:
+        d.close()
+    cpu = O.oracle().run(Q, sc["xl"], sc["yl"], sc["zl"], TAU, sc["boxes"], steps)
+    assert_bitwise(xml + " populations", f, cpu["f"])
+    assert_bitwise(xml + " density", rho, cpu["rho"])
+    assert_bitwise(xml + " velocity", u, cpu["u"])
