@@ -91,8 +91,9 @@ def test_random_state_upload_slabs():
 
 
 def _torchrun(n, *args):
+    port = 29533 + (sum(map(ord, "".join(args))) % 40)        # distinct rendezvous ports for back-to-back launches
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
-           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")] + list(args)
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py")] + list(args)
     return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
 
 
