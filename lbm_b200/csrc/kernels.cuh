@@ -269,8 +269,6 @@ __device__ __forceinline__ double link_value(const double* __restrict__ src, con
 {
     using L = Lattice<Q>;
     constexpr int qi = L::inv(q);
-    constexpr int off = 0;
-    (void) off;
     switch (k) {
     case K_NOSLIP:                                            // boundary.hpp:28
         return src[qi * g.qstride + iX];
@@ -304,8 +302,6 @@ __device__ __forceinline__ double link_value(const double* __restrict__ src, con
     case K_FREESLIP:
         return freeslip_value<Q>(src, kind, g, iX, q);
     default: {                                                // NULL / PARALLEL: stored value
-        constexpr int o = 0;
-        (void) o;
         return src[q * g.qstride + iX - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q))];
     }
     }
@@ -666,12 +662,6 @@ __global__ void halo_wait_kernel(unsigned long long* flag_a, unsigned long long*
     }
     __threadfence_system();
     if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[2 * epoch + 1]));
-}
-
-// copy one x-y plane of selected populations (halo unpack / pack)
-__global__ void copy_planes_kernel(const double* __restrict__ src, double* __restrict__ dst, int n)
-{
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 } // namespace lbmb200
