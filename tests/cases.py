@@ -111,3 +111,35 @@ def duct_profile(ny, nz, terms=60):
     for m in range(1, 2 * terms, 2):
         w += (1.0 / m ** 3) * (1 - np.cosh(m * np.pi * Yy / b) / np.cosh(m * np.pi * a / b)) * np.sin(m * np.pi * Zz / b)
     return w / w.mean()
+
+
+def random_scenario(seed, Q):
+    """A random small scenario: random sizes, 3-9 random boxes of every handler kind (faces, slabs, interior
+    blocks, overlapping, later ones overwrite earlier ones), random solid mask, random near-equilibrium state.
+    Deliberately ugly: exercises last-writer-wins, handlers inside the domain, uncovered shell cells."""
+    rng = np.random.default_rng(seed)
+    xl, yl, zl = (int(v) for v in rng.integers(3, 12, size=3))
+    kinds = [O.NOSLIP, O.MOVINGWALL, O.FREESLIP, O.OUTFLOW, O.INFLOW, O.PRESSURE, O.PARALLEL]
+    boxes = []
+    faces = ["z0", "zmax", "x0", "xmax", "y0", "ymax"]
+    rng.shuffle(faces)
+    n_faces = int(rng.integers(2, 7))
+    spec = []
+    for name in faces[:n_faces]:
+        k = int(rng.choice(kinds))
+        spec.append((name, k, tuple(rng.uniform(-0.05, 0.05, 3)), float(rng.uniform(0.95, 1.05))))
+    boxes += O.face_boxes(xl, yl, zl, spec)
+    for _ in range(int(rng.integers(1, 4))):          # interior / straddling blocks
+        lo = [int(rng.integers(0, n + 1)) for n in (xl, yl, zl)]
+        hi = [int(min(n + 1, l + rng.integers(0, 4))) for n, l in zip((xl, yl, zl), lo)]
+        k = int(rng.choice(kinds))
+        boxes.append((k, tuple(float(v) for v in rng.uniform(-0.05, 0.05, 3)), float(rng.uniform(0.95, 1.05)),
+                      (lo[0], hi[0], lo[1], hi[1], lo[2], hi[2])))
+    mask = (rng.random((zl, yl, xl)) > 0.1).astype(np.uint8) if rng.random() < 0.5 else None
+    _, w = O.oracle().model(Q)
+    n_all = (xl + 2) * (yl + 2) * (zl + 2)
+    f0 = np.tile(w, (n_all, 1)) * (1 + 0.05 * rng.standard_normal((n_all, Q)))
+    case = dict(xl=xl, yl=yl, zl=zl, boxes=boxes, f_init=f0)
+    if mask is not None:
+        case["fluid_mask"] = mask
+    return case

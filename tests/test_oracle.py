@@ -152,3 +152,19 @@ def test_mass_conservation_closed_box():
     m5 = O.oracle().run(19, n, n, n, TAU, boxes, 5, f_init=f0)["rho"].sum()
     m50 = O.oracle().run(19, n, n, n, TAU, boxes, 50, f_init=f0)["rho"].sum()
     assert abs(m50 - m5) / m5 < 1e-13
+
+
+@pytest.mark.parametrize("Q", [15, 19, 27])
+def test_fuzz_oracle_equals_compiled_reference(Q):
+    """random scenarios (every handler kind, overlapping boxes, interior handlers, masks, uncovered shell)"""
+    ref = O.ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    for seed in range(25):
+        case = cases.random_scenario(1000 * Q + seed, Q)
+        kw = {k: case[k] for k in ("f_init", "fluid_mask") if k in case}
+        steps = 6 + seed % 5
+        a = ref.run(Q, case["xl"], case["yl"], case["zl"], TAU, case["boxes"], steps, **kw)
+        b = O.oracle().run(Q, case["xl"], case["yl"], case["zl"], TAU, case["boxes"], steps, **kw)
+        for key in ("f", "rho", "u", "kind"):
+            assert same_bits(a[key], b[key]), (seed, key)

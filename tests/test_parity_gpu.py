@@ -253,3 +253,17 @@ def test_shipped_scenario_files_gpu_vs_oracle(xml, Q, steps):
     assert_bitwise(xml + " populations", f, cpu["f"])
     assert_bitwise(xml + " density", rho, cpu["rho"])
     assert_bitwise(xml + " velocity", u, cpu["u"])
+
+
+@pytest.mark.parametrize("Q", [15, 19, 27])
+def test_fuzz_random_scenarios_exact(Q):
+    """random scenarios (tests/cases.py: random_scenario): every handler kind anywhere, overlaps, masks, holes in
+    the shell -- populations, density and velocity bit-identical to the oracle"""
+    for seed in range(25):
+        case = cases.random_scenario(1000 * Q + seed, Q)
+        steps = 6 + seed % 5
+        cpu = run_cpu(Q, case, steps)
+        gpu = run_gpu(Q, case, steps, exact=True)
+        assert_bitwise("seed %d populations" % seed, gpu["f"], cpu["f"])
+        assert_bitwise("seed %d density" % seed, gpu["rho"], cpu["rho"])
+        assert_bitwise("seed %d velocity" % seed, gpu["u"], cpu["u"])
