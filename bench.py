@@ -13,7 +13,6 @@ src/main.cpp:64-65) is reported in config.mlups_reference_formula.
 Prints ONE JSON line on rank 0.
 """
 import argparse
-import ctypes
 import json
 import os
 import statistics
