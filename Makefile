@@ -4,7 +4,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 HOSTCXX   ?= /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) \
-             -Xcompiler -fPIC,-ffp-contract=off,-fopenmp,-Wall --expt-relaxed-constexpr
+             -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-enum-compare --expt-relaxed-constexpr
 LIB       := lbm_b200/liblbm_b200.so
 SRC       := lbm_b200/csrc/engine.cu
 HDR       := lbm_b200/csrc/kernels.cuh lbm_b200/csrc/lattice.cuh include/lbm_b200.h
@@ -12,7 +12,7 @@ HDR       := lbm_b200/csrc/kernels.cuh lbm_b200/csrc/lattice.cuh include/lbm_b20
 all: $(LIB)
 
 $(LIB): $(SRC) $(HDR)
-	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(SRC) -lcudart -lgomp 2> lbm_b200/csrc/ptxas.log || (cat lbm_b200/csrc/ptxas.log; false)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(SRC) -lcudart 2> lbm_b200/csrc/ptxas.log || (cat lbm_b200/csrc/ptxas.log; false)
 
 oracle:
 	$(MAKE) -C oracle

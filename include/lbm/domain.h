@@ -47,10 +47,21 @@ inline int& arithmetic_ref()
     }();
     return m;
 }
+// Handlers set through Domain::cell() -- the VTK mask reader (io/vtk.hpp:145-146),
+// set_nonfluid_cells_nullcollide (domain.hpp:108-109), Cell::set_collision_handler -- reach only the
+// collide field in the reference, so such a cell is solid on every other step.  literal = true
+// reproduces that bit for bit; the default applies them to both lattices (DESIGN.md "deviations").
+inline bool& mask_literal_ref()
+{
+    static bool b = [] { const char* e = std::getenv("LBM_B200_MASK_LITERAL"); return e && std::atoi(e) != 0; }();
+    return b;
+}
 inline void set_gpus(int n) { gpus_ref() = n < 1 ? 1 : n; }
 inline int gpus() { return gpus_ref(); }
 inline void set_arithmetic(int mode) { arithmetic_ref() = mode; }
 inline int arithmetic() { return arithmetic_ref(); }
+inline void set_mask_literal(bool on) { mask_literal_ref() = on; }
+inline bool mask_literal() { return mask_literal_ref(); }
 
 inline void check(int rc, const char* what)
 {
@@ -72,17 +83,21 @@ class Domain
     };
     std::vector<Slab> slabs;
 
-    // handler bookkeeping: id 0 is the fluid operator
+    // Handler bookkeeping.  The per-cell handler maps live on the device (one kind byte and one handler id
+    // per cell and lattice); the host keeps the table id -> handler object (id 0 is the fluid operator)
+    // and a journal of boxes not yet sent.  Applying a scenario to a 512^3 lattice therefore ships a few
+    // hundred bytes; per-cell questions (cell().get_collision_handler(), handler()) fetch one x-y plane
+    // of the maps on demand.
     std::vector<const Collision<lattice_model>*> handlers;
-    std::vector<std::uint16_t> handler_id;      // per cell, Domain::idx order
-    bool geometry_dirty { true };
-    // set_nonfluid_cells_nullcollide() tags the collide field only (domain.hpp:108-109 goes through
-    // cell()), so in the reference a buried solid cell reports NullCollision on even and its
-    // original handler on odd step counts after the call.  No effect on any population; kept so
-    // that get_collision_handler() agrees.  null_original[i] = id before tagging, NOT_TAGGED else.
-    static constexpr std::uint16_t NOT_TAGGED = 0xFFFF;
-    std::vector<std::uint16_t> null_original;
-    std::uint64_t null_tagged_at { 0 };
+    std::size_t handlers_pushed { 0 };
+    std::vector<std::uint64_t> pending_boxes;       // 6 inclusive indices per box
+    std::vector<std::uint16_t> pending_ids;
+    struct HandlerPlane {
+        std::vector<std::uint8_t> kind;
+        std::vector<std::uint16_t> id;
+        bool valid { false };
+    };
+    mutable std::vector<HandlerPlane> handler_planes;
 
     // Host mirror behind cell(): one x-y plane at a time, downloaded on first access after a step
     // and uploaded before the next step if a mutable reference into it was handed out.  Touching
@@ -91,6 +106,7 @@ class Domain
     // plane is fetched again), like references into the reference's Cell vectors.
     struct PlaneMirror {
         Lattice_field<lattice_model> cells;
+        std::vector<const Collision<lattice_model>*> fetched;   // handlers as reported when the plane was fetched
         bool valid { false };
         bool dirty { false };
     };
@@ -100,19 +116,13 @@ class Domain
     bool streamed { false }, swapped { false };
     std::uint64_t steps_done { 0 };
 
-    std::uint16_t reported_id(std::size_t i) const
+    static NullCollision<lattice_model>& null_collision()
     {
-        if (!null_original.empty() && null_original[i] != NOT_TAGGED && ((steps_done - null_tagged_at) & 1))
-            return null_original[i];
-        return handler_id[i];
-    }
-    void untag(std::size_t i)
-    {
-        if (!null_original.empty()) null_original[i] = NOT_TAGGED;
+        static NullCollision<lattice_model> instance;      // domain.hpp:103
+        return instance;
     }
 
     std::size_t plane_cells() const { return (xl + 2) * (yl + 2); }
-    std::size_t all_cells() const { return plane_cells() * (zl + 2); }
 
     std::uint16_t intern(const Collision<lattice_model>* h)
     {
@@ -126,19 +136,39 @@ class Domain
         return std::uint16_t(handlers.size() - 1);
     }
 
-    void push_geometry()
+    // handler object for what the device reports about a cell
+    const Collision<lattice_model>* decode(std::uint8_t kind, std::uint16_t id) const
     {
-        if (!geometry_dirty) return;
+        const Collision<lattice_model>* h = id < handlers.size() ? handlers[id] : collision;
+        // a cell tagged by set_nonfluid_cells_nullcollide keeps its former handler's id
+        if (kind == LBM_B200_NULL && h->device_kind() != LBM_B200_NULL) return &null_collision();
+        return h;
+    }
+
+    void push_handlers()
+    {
+        if (handlers_pushed == handlers.size()) return;
         std::vector<lbm_b200_bc> table(handlers.size());
         for (std::size_t i = 0; i < handlers.size(); ++i) table[i] = handlers[i]->descriptor();
-        std::vector<std::uint8_t> kind(all_cells());
-        for (std::size_t i = 0; i < kind.size(); ++i) kind[i] = std::uint8_t(table[handler_id[i]].kind);
-        for (auto& s : slabs) {
-            const std::size_t off = (s.z_first - 1) * plane_cells();   // local plane 0 == global plane z_first-1
-            device::check(lbm_b200_set_geometry(s.handle, kind.data() + off, handler_id.data() + off,
-                    table.data(), int(table.size())), "lbm_b200_set_geometry");
-        }
-        geometry_dirty = false;
+        for (auto& s : slabs) device::check(lbm_b200_set_handlers(s.handle, table.data(), int(table.size())), "lbm_b200_set_handlers");
+        handlers_pushed = handlers.size();
+    }
+
+    // journal -> device: the handler table and the boxes of setBoundaryCondition, in order
+    void push_geometry()
+    {
+        push_handlers();
+        if (pending_ids.empty()) return;
+        for (auto& s : slabs)
+            device::check(lbm_b200_paint_boxes(s.handle, pending_boxes.data(), pending_ids.data(), int(pending_ids.size())),
+                    "lbm_b200_paint_boxes");
+        pending_boxes.clear();
+        pending_ids.clear();
+    }
+
+    void invalidate_handler_planes() const
+    {
+        for (auto& hp : handler_planes) hp.valid = false;
     }
 
     // boundary cells next to a slab cut need the neighbour slab's full edge plane for the read-back pass
@@ -158,11 +188,20 @@ class Domain
             if (z >= slabs[i].z_first && z < slabs[i].z_first + slabs[i].zl_local) return i;
         return z == 0 ? 0 : slabs.size() - 1;
     }
-    bool any_dirty() const
+
+    // handler maps of plane z as Domain::cell() of the reference would report them
+    const HandlerPlane& fetch_handlers(std::size_t z) const
     {
-        for (const auto& pm : planes)
-            if (pm.dirty) return true;
-        return false;
+        HandlerPlane& hp = handler_planes[z];
+        if (hp.valid) return hp;
+        const_cast<Domain*>(this)->push_geometry();
+        hp.kind.resize(plane_cells());
+        hp.id.resize(plane_cells());
+        const Slab& s = slabs[owner_of(z)];
+        device::check(lbm_b200_get_geometry_planes(s.handle, hp.kind.data(), hp.id.data(), z - (s.z_first - 1), 1),
+                "lbm_b200_get_geometry_planes");
+        hp.valid = true;
+        return hp;
     }
 
     // mirror <- device
@@ -178,13 +217,16 @@ class Domain
         }
         constexpr std::size_t Q = lattice_model::Q;
         if (pm.cells.empty()) pm.cells.assign(plane_cells(), Cell<lattice_model>(collision));
+        pm.fetched.resize(plane_cells());
         const Slab& s = slabs[owner_of(z)];
         std::vector<double> buf(plane_cells() * Q);
         device::check(lbm_b200_download_planes(s.handle, buf.data(), LBM_B200_COLLIDE_FIELD, z - (s.z_first - 1), 1),
                 "lbm_b200_download_planes");
+        const HandlerPlane& hp = fetch_handlers(z);
         for (std::size_t c = 0; c < plane_cells(); ++c) {
             std::memcpy(pm.cells[c].data(), buf.data() + c * Q, Q * sizeof(double));
-            pm.cells[c].set_collision_handler(handlers[reported_id(z * plane_cells() + c)]);
+            pm.fetched[c] = decode(hp.kind[c], hp.id[c]);
+            pm.cells[c].set_collision_handler(pm.fetched[c]);
         }
         pm.valid = true;
         pm.dirty = false;
@@ -198,15 +240,36 @@ class Domain
         for (std::size_t z = 0; z < planes.size(); ++z) {
             PlaneMirror& pm = planes[z];
             if (!pm.dirty) continue;
-            // handlers may have been changed through Cell::set_collision_handler
-            for (std::size_t c = 0; c < plane_cells(); ++c) {
-                const std::size_t i = z * plane_cells() + c;
-                const auto* h = pm.cells[c].get_collision_handler();
-                if (h != handlers[reported_id(i)]) {
-                    handler_id[i] = intern(h);
-                    untag(i);
-                    geometry_dirty = true;
+            // handlers changed through Cell::set_collision_handler
+            std::vector<std::size_t> changed;
+            for (std::size_t c = 0; c < plane_cells(); ++c)
+                if (pm.cells[c].get_collision_handler() != pm.fetched[c]) changed.push_back(c);
+            if (!changed.empty()) {
+                push_geometry();                       // earlier boxes first
+                if (device::mask_literal()) {
+                    // the reference writes the collide field's handler only (cell.h:62-63 through domain.hpp:74-83)
+                    HandlerPlane hp = fetch_handlers(z);
+                    for (auto c : changed) {
+                        const auto* h = pm.cells[c].get_collision_handler();
+                        hp.id[c] = intern(h);
+                        hp.kind[c] = std::uint8_t(h->device_kind());
+                    }
+                    push_handlers();
+                    for (auto& s : slabs)
+                        if (z + 1 >= s.z_first && z <= s.z_first + s.zl_local)
+                            device::check(lbm_b200_set_geometry_planes(s.handle, hp.kind.data(), hp.id.data(), z - (s.z_first - 1), 1, 1),
+                                    "lbm_b200_set_geometry_planes");
+                } else {
+                    for (auto c : changed) {
+                        const std::uint64_t x = c % (xl + 2), y = c / (xl + 2);
+                        const std::uint64_t box[6] = { x, x, y, y, z, z };
+                        pending_boxes.insert(pending_boxes.end(), box, box + 6);
+                        pending_ids.push_back(intern(pm.cells[c].get_collision_handler()));
+                    }
+                    push_geometry();
                 }
+                for (auto c : changed) pm.fetched[c] = pm.cells[c].get_collision_handler();
+                handler_planes[z].valid = false;
             }
             buf.resize(plane_cells() * Q);
             for (std::size_t c = 0; c < plane_cells(); ++c) std::memcpy(buf.data() + c * Q, pm.cells[c].data(), Q * sizeof(double));
@@ -243,8 +306,9 @@ public:
             throw std::logic_error("Domain: only BGKCollision can run in the CUDA sweep (the reference asserts "
                     "collision-model == bgk as well, io/configuration.h:126-128)");
         handlers.push_back(collision);
-        handler_id.assign(all_cells(), 0);
+        handlers_pushed = 1;            // a fresh handle's table already holds the fluid operator as id 0
         planes.resize(zl + 2);
+        handler_planes.resize(zl + 2);
         int n = device::gpus();
         if (std::size_t(n) > zl) n = int(zl);
         const int visible = lbm_b200_device_count();
@@ -313,46 +377,27 @@ public:
     // handler of a cell without touching the population mirror
     auto handler(int x, int y, int z) const -> const Collision<lattice_model>*
     {
+        const std::size_t c = std::size_t(x) + (xl + 2) * std::size_t(y);
         const PlaneMirror& pm = planes[std::size_t(z)];
-        if (pm.valid && pm.dirty) return pm.cells[std::size_t(x) + (xl + 2) * std::size_t(y)].get_collision_handler();
-        return handlers[reported_id(std::size_t(idx(x, y, z)))];
+        if (pm.valid && pm.dirty) return pm.cells[c].get_collision_handler();
+        const HandlerPlane& hp = fetch_handlers(std::size_t(z));
+        return decode(hp.kind[c], hp.id[c]);
     }
 
     // domain.hpp:101-113: interior non-fluid cells without any interior fluid neighbour get the
     // do-nothing handler.  A pure optimisation in the reference; the device sweep never visits
-    // such cells anyway, so only the handler bookkeeping changes.
+    // such cells anyway, so only the handler maps change (on the device, one kernel).
     auto set_nonfluid_cells_nullcollide() -> void
     {
         require_idle("set_nonfluid_cells_nullcollide()");
         push_mirror();
-        static NullCollision<lattice_model> null_collision;
-        std::vector<std::size_t> lonely;
-        for (int z = 1; z < int(zl) + 1; ++z)
-            for (int y = 1; y < int(yl) + 1; ++y)
-                for (int x = 1; x < int(xl) + 1; ++x) {
-                    if (handlers[handler_id[idx(x, y, z)]]->is_fluid()) continue;
-                    bool vicinity = false;
-                    for (std::size_t q = 0; q < lattice_model::Q && !vicinity; ++q) {
-                        const int nx = x + int(lattice_model::velocities[q][0]);
-                        const int ny = y + int(lattice_model::velocities[q][1]);
-                        const int nz = z + int(lattice_model::velocities[q][2]);
-                        vicinity = in_bounds(nx, ny, nz) && handlers[handler_id[idx(nx, ny, nz)]]->is_fluid();
-                    }
-                    if (!vicinity) lonely.push_back(std::size_t(idx(x, y, z)));
-                }
-        if (lonely.empty()) return;
-        const std::uint16_t id = intern(&null_collision);
-        if (null_original.empty()) null_original.assign(all_cells(), NOT_TAGGED);
-        null_tagged_at = steps_done;
-        for (auto i : lonely) {
-            if (handler_id[i] != id) null_original[i] = handler_id[i];
-            handler_id[i] = id;
+        push_geometry();
+        for (auto& s : slabs) {
+            std::uint64_t tagged = 0;
+            device::check(lbm_b200_tag_null_cells(s.handle, device::mask_literal() ? 1 : 0, &tagged), "lbm_b200_tag_null_cells");
         }
-        for (auto i : lonely) {
-            PlaneMirror& pm = planes[i / plane_cells()];
-            if (pm.valid) pm.cells[i % plane_cells()].set_collision_handler(&null_collision);
-        }
-        geometry_dirty = true;
+        invalidate_handler_planes();
+        for (auto& pm : planes) pm.valid = false;     // handlers of mirrored cells are refreshed on the next access
     }
 
     // domain.hpp:175-194: inclusive box, later calls overwrite earlier ones
@@ -364,19 +409,34 @@ public:
             throw std::out_of_range("setBoundaryCondition: extent outside the domain (the reference asserts this, domain.hpp:180-181)");
         push_mirror();
         const std::uint16_t id = intern(&condition);
-        for (auto z = z0; z <= zE; ++z)
-            for (auto y = y0; y <= yE; ++y)
-                for (auto x = x0; x <= xE; ++x) {
-                    handler_id[std::size_t(idx(int(x), int(y), int(z)))] = id;
-                    untag(std::size_t(idx(int(x), int(y), int(z))));
-                }
+        const std::uint64_t box[6] = { x0, xE, y0, yE, z0, zE };
+        pending_boxes.insert(pending_boxes.end(), box, box + 6);
+        pending_ids.push_back(id);
         for (auto z = z0; z <= zE; ++z) {
+            handler_planes[z].valid = false;
             PlaneMirror& pm = planes[z];
             if (!pm.valid) continue;
             for (auto y = y0; y <= yE; ++y)
-                for (auto x = x0; x <= xE; ++x) pm.cells[x + (xl + 2) * y].set_collision_handler(&condition);
+                for (auto x = x0; x <= xE; ++x) {
+                    pm.cells[x + (xl + 2) * y].set_collision_handler(&condition);
+                    pm.fetched[x + (xl + 2) * y] = &condition;
+                }
         }
-        geometry_dirty = true;
+    }
+
+    // the mask loop of io/vtk.hpp:141-150 in one call: interior cells whose mask byte is 0 (x fastest, then y,
+    // then z, like the POINT_DATA of the file) take `solid`.  With device::mask_literal() the handler reaches
+    // the collide field only, as Domain::cell(x,y,z).set_collision_handler(&solid) does in the reference.
+    auto apply_fluid_mask(const std::uint8_t* mask, NonFluidCollision<lattice_model>& solid) -> void
+    {
+        require_idle("apply_fluid_mask()");
+        push_mirror();
+        const std::uint16_t id = intern(&solid);
+        push_geometry();
+        for (auto& s : slabs)
+            device::check(lbm_b200_paint_mask(s.handle, mask, id, device::mask_literal() ? 1 : 0), "lbm_b200_paint_mask");
+        invalidate_handler_planes();
+        for (auto& pm : planes) pm.valid = false;
     }
 
     // Iteration functions.  The reference runs three host loops (domain.hpp:116-172); here
@@ -411,11 +471,15 @@ public:
         if (slabs.size() == 1) {
             device::check(lbm_b200_step(slabs[0].handle, n), "lbm_b200_step");
         } else {
-            for (std::uint64_t t = 0; t < n; ++t)
-                for (auto& s : slabs) device::check(lbm_b200_step(s.handle, 1), "lbm_b200_step");
+            std::vector<lbm_b200_t*> hs;
+            for (auto& s : slabs) hs.push_back(s.handle);
+            device::check(lbm_b200_step_group(hs.data(), int(hs.size()), n), "lbm_b200_step_group");
         }
         steps_done += n;
-        if (n > 0) invalidate_mirror();
+        if (n > 0) {
+            invalidate_mirror();
+            invalidate_handler_planes();     // tags of set_nonfluid_cells_nullcollide alternate with the swaps
+        }
     }
     auto synchronize() const -> void
     {
@@ -438,6 +502,29 @@ public:
             device::check(lbm_b200_macroscopic(s.handle, rho ? rho + off : nullptr, u ? u + 3 * off : nullptr),
                     "lbm_b200_macroscopic");
         }
+    }
+    // split form: reduce now, copy while later steps run, wait in macroscopic_end() (rho / u should be
+    // page-locked, see lbm_b200_host_alloc).  Multi-slab domains: call synchronize-free after macroscopic()
+    // has been used once for this time level only if no boundary cell next to a cut matters.
+    auto macroscopic_begin(double* rho, double* u) const -> void
+    {
+        require_idle("macroscopic_begin()");
+        auto* self = const_cast<Domain*>(this);
+        self->push_mirror();
+        self->push_geometry();
+        if (!readback_ready) {
+            prepare_readback();
+            readback_ready = true;
+        }
+        for (auto& s : slabs) {
+            const std::size_t off = (s.z_first - 1) * xl * yl;
+            device::check(lbm_b200_macroscopic_begin(s.handle, rho ? rho + off : nullptr, u ? u + 3 * off : nullptr),
+                    "lbm_b200_macroscopic_begin");
+        }
+    }
+    auto macroscopic_end() const -> void
+    {
+        for (auto& s : slabs) device::check(lbm_b200_macroscopic_end(s.handle), "lbm_b200_macroscopic_end");
     }
     auto gpu_count() const -> std::size_t { return slabs.size(); }
     auto timesteps_done() const -> std::uint64_t { return steps_done; }

@@ -10,10 +10,11 @@
 //                        LBM_VTS_ASCII is defined) -- readable by ParaView like the
 //                        reference's output.
 //   read_vtk_point_file  legacy-VTK ASCII STRUCTURED_POINTS fluid mask -> Domain with
-//                        solid cells tagged, as io/vtk.hpp:94-157.  Deviation: the
-//                        reference tags the collide field only (vtk.hpp:145-146), which
-//                        makes masked cells flip between solid and fluid on every swap();
-//                        here a masked cell is solid in both lattices.
+//                        solid cells tagged, as io/vtk.hpp:94-157.  The reference tags the
+//                        collide field only (vtk.hpp:145-146), which makes masked cells flip
+//                        between solid and fluid on every swap(); that behaviour is opt-in
+//                        (lbm::device::set_mask_literal / LBM_B200_MASK_LITERAL=1, bit-identical
+//                        to the reference); by default a masked cell is solid in both lattices.
 #pragma once
 #include <cctype>
 #include <cstdint>
@@ -146,24 +147,14 @@ auto read_vtk_point_file(const std::string& filename, FluidCollision<lattice_mod
     auto domain = make_unique<Domain<lattice_model>>(dims[0], dims[1], dims[2], fluid_collision_model,
             origin[0], origin[1], origin[2], spacing[0], spacing[1], spacing[2]);
     auto& solid = BoundaryKeeper<lattice_model>::template get_collision<solid_collision_model>(*domain);
-    // interior cells only, linearly, x fastest; runs of solid cells become one box each
-    for (long z = 1; z < dims[2] + 1; ++z)
-        for (long y = 1; y < dims[1] + 1; ++y) {
-            long run_start = -1;
-            for (long x = 1; x <= dims[0] + 1; ++x) {
-                bool fluid = true;
-                if (x <= dims[0]) {
-                    int v;
-                    if (!(in >> v)) throw std::logic_error("Could not read file!");
-                    fluid = v != 0;
-                }
-                if (!fluid && run_start < 0) run_start = x;
-                if (fluid && run_start >= 0) {
-                    domain->setBoundaryCondition(solid, run_start, x - 1, y, y, z, z);
-                    run_start = -1;
-                }
-            }
-        }
+    // interior cells only, linearly, x fastest (io/vtk.hpp:141-150); the mask is painted on the device
+    std::vector<std::uint8_t> mask(expected);
+    for (std::size_t i = 0; i < expected; ++i) {
+        int v;
+        if (!(in >> v)) throw std::logic_error("Could not read file!");
+        mask[i] = v != 0;
+    }
+    domain->apply_fluid_mask(mask.data(), solid);
     return domain;
 }
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define LBM_B200_ABI_VERSION 1
+#define LBM_B200_ABI_VERSION 2
 
 /* error codes */
 enum {
@@ -125,21 +125,60 @@ int lbm_b200_set_tau(lbm_b200_t* h, double tau);
  * returns to the handle's own stream */
 int lbm_b200_set_stream(lbm_b200_t* h, void* cuda_stream);
 
-/* --- geometry (Domain::setBoundaryCondition, domain.hpp:175-194, and
- *     Domain::set_nonfluid_cells_nullcollide, domain.hpp:101-113) ------------ */
-/* kind: one LBM_B200_* per local cell; bc_id: index into table for cells whose
- * kind takes parameters (may be NULL if n_table <= 1; then id 0 is used). */
+/* --- geometry (Domain::setBoundaryCondition, domain.hpp:175-194;
+ *     Domain::set_nonfluid_cells_nullcollide, domain.hpp:101-113; the mask loop of
+ *     io/vtk.hpp:137-150) -------------------------------------------------------
+ * The handler maps live on the DEVICE (one kind byte + one handler id per cell of
+ * each lattice); boxes and masks are painted there by small kernels, so applying a
+ * scenario to a 512^3 lattice moves a few hundred bytes over PCIe, not the maps.
+ *
+ * Handlers belong to lattices in the reference (cell.h:15).  setBoundaryCondition
+ * writes both lattices; everything that goes through Domain::cell() -- the VTK mask
+ * reader, set_nonfluid_cells_nullcollide, Cell::set_collision_handler -- writes the
+ * collide field only, after which such a cell is solid on every other step.  The
+ * `literal` arguments below select that behaviour (bit-identical to the reference);
+ * literal = 0 writes both lattices.  Literal edits are limited to whole domains
+ * (not slabs). */
+/* the handler table (what BoundaryKeeper owns, boundary.h:75-91): ids stored in the
+ * maps index it.  Replaces the table; ids already used by cells keep their meaning,
+ * so a new table must extend the old one. */
+int lbm_b200_set_handlers(lbm_b200_t* h, const lbm_b200_bc* table, int n_table);
+/* setBoundaryCondition for n boxes applied in order, last writer wins
+ * (io/scenario.h:91-128 -> domain.hpp:185-193): box i = 6 inclusive GLOBAL indices
+ * x0,xE,y0,yE,z0,zE, painted with handler ids[i] of the table (kind = table kind). */
+int lbm_b200_paint_boxes(lbm_b200_t* h, const uint64_t* boxes6, const uint16_t* ids, int n);
+/* convenience: appends table[0..n) to the handler table and paints box i with it */
+int lbm_b200_set_boxes(lbm_b200_t* h, const uint64_t* boxes6, const lbm_b200_bc* table, int n);
+/* dense maps for every local cell (Domain::idx order): kind = one LBM_B200_* per cell,
+ * bc_id = index into table for cells whose kind takes parameters (may be NULL if
+ * n_table <= 1; then id 0 is used).  Replaces table and maps of both lattices; the
+ * maps are checked on the device and rejected as a whole if inconsistent. */
 int lbm_b200_set_geometry(lbm_b200_t* h, const uint8_t* kind, const uint16_t* bc_id,
                           const lbm_b200_bc* table, int n_table);
-/* the same through boxes applied in order, last writer wins (io/scenario.h:
- * 91-128 -> domain.hpp:185-193); box i = 6 inclusive GLOBAL indices
- * x0,xE,y0,yE,z0,zE and uses table[i].  Starts from the current geometry. */
-int lbm_b200_set_boxes(lbm_b200_t* h, const uint64_t* boxes6, const lbm_b200_bc* table, int n);
-/* interior fluid mask like the POINT_DATA of a legacy-VTK file (io/vtk.hpp:
- * 137-150): xl*yl*zl_local bytes, 0 => NoSlipBoundary.  Applied to BOTH lattices
- * (the reference tags the collide field only; see DESIGN.md "deviations"). */
+/* the same for the local x-y planes [z_begin, z_begin+z_count) only, against the current
+ * handler table: what Domain::cell(...).set_collision_handler() edits turn into */
+int lbm_b200_set_geometry_planes(lbm_b200_t* h, const uint8_t* kind, const uint16_t* bc_id,
+                                 uint64_t z_begin, uint64_t z_count, int literal);
+/* handler kinds / ids of the collide field as Domain::cell() reports them, planes
+ * [z_begin, z_begin+z_count) (either output may be NULL) */
+int lbm_b200_get_geometry_planes(lbm_b200_t* h, uint8_t* kind, uint16_t* bc_id, uint64_t z_begin, uint64_t z_count);
+int lbm_b200_get_kind(lbm_b200_t* h, uint8_t* kind);   /* all local planes */
+/* interior fluid mask like the POINT_DATA of a legacy-VTK file (io/vtk.hpp:137-150):
+ * 0 => NoSlipBoundary.  set_fluid_mask: xl*yl*zl_local bytes for this handle's own
+ * interior planes, both lattices (DESIGN.md "deviations").  _literal: the same on the
+ * collide field only, exactly as io/vtk.hpp:145-146.  _global: the mask of the WHOLE
+ * domain (xl*yl*zl_global bytes); a slab takes its own planes and the replicas of its
+ * neighbours' edge planes from it. */
 int lbm_b200_set_fluid_mask(lbm_b200_t* h, const uint8_t* mask);
-int lbm_b200_get_kind(lbm_b200_t* h, uint8_t* kind);
+int lbm_b200_set_fluid_mask_literal(lbm_b200_t* h, const uint8_t* mask);
+int lbm_b200_set_fluid_mask_global(lbm_b200_t* h, const uint8_t* mask, int literal);
+/* the same with a handler of the table instead of an implicit NoSlipBoundary (whole-domain mask) */
+int lbm_b200_paint_mask(lbm_b200_t* h, const uint8_t* mask, uint16_t id, int literal);
+/* Domain::set_nonfluid_cells_nullcollide on the device; *n_tagged = cells newly tagged.
+ * The reference tags the collide field only, so Domain::cell() reports NullCollision on
+ * even and the former handler on odd step counts after the call; get_geometry_planes
+ * reproduces that.  No population ever depends on the tag. */
+int lbm_b200_tag_null_cells(lbm_b200_t* h, int literal, uint64_t* n_tagged);
 
 /* --- state ------------------------------------------------------------------ */
 int lbm_b200_upload_populations(lbm_b200_t* h, const double* f, int layout, int field);
@@ -153,8 +192,10 @@ int lbm_b200_download_planes(lbm_b200_t* h, double* f, int field, uint64_t z_beg
  * (collision.hpp:34-51 via Cell::equilibrium, cell.hpp:55-59) */
 int lbm_b200_init_equilibrium(lbm_b200_t* h, const double* rho, const double* u);
 
-/* checkpoint / restart of one slab (not in the reference): the collide field incl. boundary
- * cells as the reference holds them, plus the step counter.  Geometry is not stored: re-apply it first. */
+/* checkpoint / restart of one slab (not in the reference): both lattices incl. boundary
+ * cells as the reference holds them, the step counter, the arithmetic mode and a checksum of the handler
+ * maps.  Geometry itself is not stored: re-apply it first; loading under another geometry, lattice or
+ * arithmetic mode is refused. */
 int lbm_b200_save_checkpoint(lbm_b200_t* h, const char* path);
 int lbm_b200_load_checkpoint(lbm_b200_t* h, const char* path);
 
@@ -167,21 +208,40 @@ int lbm_b200_elapsed_ms(lbm_b200_t* h, double* ms);
 int lbm_b200_launch_count(lbm_b200_t* h, uint64_t* n);
 uint64_t lbm_b200_steps_done(lbm_b200_t* h);
 
+/* n time steps of a whole stack of connected slabs (handles[0..n_handles), any devices) from one host
+ * thread: the slabs' steps are enqueued interleaved in short runs so that no device queue ever waits
+ * for work that has not been submitted yet.  What Domain::step() calls for a multi-GPU Domain. */
+int lbm_b200_step_group(lbm_b200_t* const* handles, int n_handles, uint64_t n_steps);
+/* replay runs of steps from CUDA graphs (1 = always, 0 = never, -1 = automatic: small lattices, where
+ * the launch overhead matters) */
+int lbm_b200_set_graphs(lbm_b200_t* h, int mode);
+
 /* --- read-out (io/vtk.hpp:62-73): interior cells, z,y,x order --------------- */
 /* rho: xl*yl*zl_local doubles, u: 3x that (may each be NULL) */
 int lbm_b200_macroscopic(lbm_b200_t* h, double* rho, double* u);
+/* split form: _begin reduces density / velocity of the CURRENT time level on the device and starts the
+ * copies to the host on a second stream; steps issued afterwards overlap with the transfer; _end waits
+ * until rho / u are complete.  (One output interval of src/main.cpp:48-57 without stalling the time
+ * loop.)  rho / u should be pinned memory (lbm_b200_host_alloc) for the copy to be asynchronous. */
+int lbm_b200_macroscopic_begin(lbm_b200_t* h, double* rho, double* u);
+int lbm_b200_macroscopic_end(lbm_b200_t* h);
+/* page-locked host memory placed on the NUMA node next to `device` (device < 0: the current one) */
+int lbm_b200_host_alloc(void** ptr, size_t bytes, int device);
+int lbm_b200_host_free(void* ptr);
+/* pins the calling host thread to the CPUs next to `device` (no-op where the topology is unknown) */
+int lbm_b200_bind_host_thread(int device);
 /* reductions for physics checks: sum of density, sum of |u|^2, max |u| over
  * interior FLUID cells of this slab */
 int lbm_b200_diagnostics(lbm_b200_t* h, double* mass, double* kinetic, double* umax);
 
 /* --- multi-GPU z-slabs -------------------------------------------------------
  * After a step, slab r's top interior plane populations with c_z=+1 must appear
- * in slab r+1's bottom ghost plane and vice versa.  Three transports:
+ * in slab r+1's bottom ghost plane and vice versa.  Two transports:
  *  (1) split-phase with an external transport (NCCL through torch.distributed):
  *        step_edges -> [send/recv the halo planes] -> step_interior -> step_finish
  *  (2) direct peer stores from the sweep kernel (CUDA P2P in one process, CUDA
  *      IPC across processes): connect once, then lbm_b200_step as usual;
- *  (3) in-process helper lbm_b200_group_* driving N slabs from one host thread.
+ *      in one process lbm_b200_step_group drives the whole stack from one host thread.
  */
 enum { LBM_B200_DOWN = 0, LBM_B200_UP = 1 };
 /* number of populations crossing an interface per direction (5/5/9) and the

@@ -27,11 +27,15 @@ SYMBOLS = [
     "lbm_b200_model", "lbm_b200_model_inv", "lbm_b200_model_velocity_index",
     "lbm_b200_create", "lbm_b200_create_slab", "lbm_b200_destroy",
     "lbm_b200_set_arithmetic", "lbm_b200_set_tau", "lbm_b200_set_stream",
-    "lbm_b200_set_geometry", "lbm_b200_set_boxes", "lbm_b200_set_fluid_mask", "lbm_b200_get_kind",
+    "lbm_b200_set_handlers", "lbm_b200_paint_boxes", "lbm_b200_set_boxes", "lbm_b200_set_geometry",
+    "lbm_b200_set_geometry_planes", "lbm_b200_get_geometry_planes", "lbm_b200_get_kind",
+    "lbm_b200_set_fluid_mask", "lbm_b200_set_fluid_mask_literal", "lbm_b200_set_fluid_mask_global",
+    "lbm_b200_paint_mask", "lbm_b200_tag_null_cells",
     "lbm_b200_upload_populations", "lbm_b200_download_populations", "lbm_b200_init_equilibrium",
     "lbm_b200_save_checkpoint", "lbm_b200_load_checkpoint", "lbm_b200_upload_planes", "lbm_b200_download_planes",
-    "lbm_b200_step", "lbm_b200_sync", "lbm_b200_elapsed_ms", "lbm_b200_launch_count", "lbm_b200_steps_done",
-    "lbm_b200_macroscopic", "lbm_b200_diagnostics",
+    "lbm_b200_step", "lbm_b200_step_group", "lbm_b200_set_graphs", "lbm_b200_sync", "lbm_b200_elapsed_ms", "lbm_b200_launch_count", "lbm_b200_steps_done",
+    "lbm_b200_macroscopic", "lbm_b200_macroscopic_begin", "lbm_b200_macroscopic_end", "lbm_b200_diagnostics",
+    "lbm_b200_host_alloc", "lbm_b200_host_free", "lbm_b200_bind_host_thread",
     "lbm_b200_halo_layout", "lbm_b200_halo_plane", "lbm_b200_dst_buffer",
     "lbm_b200_step_edges", "lbm_b200_step_interior", "lbm_b200_step_finish",
     "lbm_b200_export", "lbm_b200_connect", "lbm_b200_connect_local", "lbm_b200_halo_push_all", "lbm_b200_halo_pushed",
@@ -68,8 +72,23 @@ lib.lbm_b200_set_tau.argtypes = [_H, C.c_double]
 lib.lbm_b200_set_stream.argtypes = [_H, C.c_void_p]
 lib.lbm_b200_set_geometry.argtypes = [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
 lib.lbm_b200_set_boxes.argtypes = [_H, C.c_void_p, C.c_void_p, C.c_int]
+lib.lbm_b200_set_handlers.argtypes = [_H, C.c_void_p, C.c_int]
+lib.lbm_b200_paint_boxes.argtypes = [_H, C.c_void_p, C.c_void_p, C.c_int]
+lib.lbm_b200_set_geometry_planes.argtypes = [_H, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]
+lib.lbm_b200_get_geometry_planes.argtypes = [_H, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
 lib.lbm_b200_set_fluid_mask.argtypes = [_H, C.c_void_p]
+lib.lbm_b200_set_fluid_mask_literal.argtypes = [_H, C.c_void_p]
+lib.lbm_b200_set_fluid_mask_global.argtypes = [_H, C.c_void_p, C.c_int]
+lib.lbm_b200_paint_mask.argtypes = [_H, C.c_void_p, C.c_uint16, C.c_int]
+lib.lbm_b200_tag_null_cells.argtypes = [_H, C.c_int, C.POINTER(C.c_uint64)]
 lib.lbm_b200_get_kind.argtypes = [_H, C.c_void_p]
+lib.lbm_b200_step_group.argtypes = [C.POINTER(_H), C.c_int, C.c_uint64]
+lib.lbm_b200_set_graphs.argtypes = [_H, C.c_int]
+lib.lbm_b200_macroscopic_begin.argtypes = [_H, C.c_void_p, C.c_void_p]
+lib.lbm_b200_macroscopic_end.argtypes = [_H]
+lib.lbm_b200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
+lib.lbm_b200_host_free.argtypes = [C.c_void_p]
+lib.lbm_b200_bind_host_thread.argtypes = [C.c_int]
 lib.lbm_b200_upload_populations.argtypes = [_H, C.c_void_p, C.c_int, C.c_int]
 lib.lbm_b200_download_populations.argtypes = [_H, C.c_void_p, C.c_int, C.c_int]
 lib.lbm_b200_init_equilibrium.argtypes = [_H, C.c_void_p, C.c_void_p]
@@ -212,10 +231,55 @@ class Domain:
         _check(lib.lbm_b200_set_geometry(self._h, kind.ctypes.data, bid.ctypes.data if bid is not None else None,
                                          C.cast(tab, C.c_void_p), len(table)))
 
-    def set_fluid_mask(self, mask):
+    def set_handlers(self, table):
+        """table: list of (kind, v3, rho); replaces (extends) the handler table"""
+        _, tab = _boxes_arrays([(k, v, rho, (0,) * 6) for (k, v, rho) in table])
+        _check(lib.lbm_b200_set_handlers(self._h, C.cast(tab, C.c_void_p), len(table)))
+
+    def paint_boxes(self, extents, ids):
+        ext = np.ascontiguousarray(extents, dtype=np.uint64).reshape(-1, 6)
+        ids = np.ascontiguousarray(ids, dtype=np.uint16).reshape(-1)
+        assert ext.shape[0] == ids.size
+        _check(lib.lbm_b200_paint_boxes(self._h, ext.ctypes.data, ids.ctypes.data, ids.size))
+
+    def set_geometry_planes(self, kind, bc_id, z_begin, z_count, literal=False):
+        kind = np.ascontiguousarray(kind, dtype=np.uint8).reshape(-1)
+        bid = np.ascontiguousarray(bc_id, dtype=np.uint16).reshape(-1)
+        assert kind.size == bid.size == z_count * (self.yl + 2) * (self.xl + 2)
+        _check(lib.lbm_b200_set_geometry_planes(self._h, kind.ctypes.data, bid.ctypes.data, z_begin, z_count, int(literal)))
+
+    def geometry_planes(self, z_begin=0, z_count=None):
+        """(kind, handler id) of the collide field as Domain::cell() reports them"""
+        if z_count is None:
+            z_count = self.zl + 2 - z_begin
+        n = z_count * (self.yl + 2) * (self.xl + 2)
+        k = np.empty(n, dtype=np.uint8)
+        b = np.empty(n, dtype=np.uint16)
+        _check(lib.lbm_b200_get_geometry_planes(self._h, k.ctypes.data, b.ctypes.data, z_begin, z_count))
+        return k, b
+
+    def set_fluid_mask(self, mask, literal=False):
+        """mask of this handle's own interior planes (io/vtk.hpp:137-150); literal: collide field only"""
         m = np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
         assert m.size == self.xl * self.yl * self.zl
-        _check(lib.lbm_b200_set_fluid_mask(self._h, m.ctypes.data))
+        if literal:
+            _check(lib.lbm_b200_set_fluid_mask_literal(self._h, m.ctypes.data))
+        else:
+            _check(lib.lbm_b200_set_fluid_mask(self._h, m.ctypes.data))
+
+    def set_fluid_mask_global(self, mask, literal=False):
+        """mask of the WHOLE domain; a slab picks its planes and its neighbours' edge planes"""
+        m = np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
+        assert m.size == self.xl * self.yl * self.zl_global
+        _check(lib.lbm_b200_set_fluid_mask_global(self._h, m.ctypes.data, int(literal)))
+
+    def tag_null_cells(self, literal=False):
+        n = C.c_uint64()
+        _check(lib.lbm_b200_tag_null_cells(self._h, int(literal), C.byref(n)))
+        return n.value
+
+    def set_graphs(self, mode):
+        _check(lib.lbm_b200_set_graphs(self._h, mode))
 
     def kind(self):
         k = np.empty(self.ncell, dtype=np.uint8)
@@ -286,6 +350,13 @@ class Domain:
         _check(lib.lbm_b200_macroscopic(self._h, rho.ctypes.data, u.ctypes.data))
         return rho, u
 
+    def macroscopic_begin(self, rho_ptr, u_ptr):
+        """split read-out into caller-owned (pinned) host memory given as raw addresses"""
+        _check(lib.lbm_b200_macroscopic_begin(self._h, C.c_void_p(rho_ptr or 0), C.c_void_p(u_ptr or 0)))
+
+    def macroscopic_end(self):
+        _check(lib.lbm_b200_macroscopic_end(self._h))
+
     def diagnostics(self):
         m, k, um = C.c_double(), C.c_double(), C.c_double()
         _check(lib.lbm_b200_diagnostics(self._h, C.byref(m), C.byref(k), C.byref(um)))
@@ -333,3 +404,36 @@ class Domain:
 
     def halo_pushed(self):
         _check(lib.lbm_b200_halo_pushed(self._h))
+
+
+def step_group(domains, n):
+    """n steps of a stack of connected slabs from one host thread (lbm_b200_step_group)"""
+    arr = (_H * len(domains))(*[d._h for d in domains])
+    _check(lib.lbm_b200_step_group(arr, len(domains), n))
+
+
+class HostBuffer:
+    """page-locked host array next to a GPU (lbm_b200_host_alloc), exposed as a numpy array"""
+
+    def __init__(self, n, dtype=np.float64, device=-1):
+        self.ptr = C.c_void_p()
+        self.nbytes = int(n) * np.dtype(dtype).itemsize
+        _check(lib.lbm_b200_host_alloc(C.byref(self.ptr), max(self.nbytes, 1), device))
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    @property
+    def address(self):
+        return self.ptr.value
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib.lbm_b200_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

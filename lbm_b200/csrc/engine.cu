@@ -4,6 +4,8 @@
 // B200.  The reference's stream(); swap(); collide(); (src/main.cpp:50-52) is a
 // single launch of sweep_kernel per step plus a buffer-index flip.
 #include <cuda_runtime.h>
+#include <sched.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -11,6 +13,8 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -82,6 +86,22 @@ auto dispatch_q(int Q, F&& f)
 
 } // namespace
 
+// Handler maps of ONE lattice (the reference keeps a handler pointer in every Cell of each of its two
+// Lattice_fields, cell.h:15).  layer[b] belongs to the physical buffer f[b].  Unless a "literal" edit made
+// the lattices differ, both layers alias the same arrays.
+struct GeoLayer {
+    uint8_t* kind = nullptr;
+    uint16_t* bcid = nullptr;
+    uint32_t* mask = nullptr;      // link mask of the steps whose SOURCE is this buffer
+    uint32_t* bits = nullptr;
+    int* inplace = nullptr;        // cells BGK-collided in place when this buffer is the DESTINATION
+    int n_inplace = 0;
+    int* wall = nullptr;           // streamed cells with a non-zero link mask (steps whose SOURCE is this buffer), sorted
+    int n_wall = 0;
+    int wall_lo = 0, wall_hi = 0;  // how many of them lie in the first / last interior plane
+    double flagged = 0.0;          // fraction of the interior cells whose bit is set (wall cells + cells not streamed)
+};
+
 struct lbm_b200 {
     int Q = 0;
     int device = 0;
@@ -93,21 +113,16 @@ struct lbm_b200 {
 
     double* f[2] = { nullptr, nullptr };
     int cur = 0;               // f[cur] is the collide field
-    uint32_t* d_mask = nullptr;
-    uint32_t* d_bits = nullptr;
-    uint8_t* d_kind = nullptr;
-    uint16_t* d_bcid = nullptr;
+    GeoLayer layer[2];
+    bool split = false;        // the two lattices carry different handlers
     BcRec* d_bc = nullptr;
-    int* d_ghost = nullptr;
-    int n_ghost = 0;
-
-    std::vector<uint8_t> h_kind;     // dense, local idx order
-    std::vector<uint16_t> h_bcid;
-    std::vector<lbm_b200_bc> h_bc;
+    int d_bc_cap = 0;
+    std::vector<lbm_b200_bc> h_bc;   // the handler table
     bool geom_dirty = true;
-    bool geom_unchecked = false;   // maps supplied as arrays, not validated yet
-    uint8_t* stage_kind = nullptr; // dense copies already on the device (set_geometry), consumed by commit
-    uint16_t* stage_bcid = nullptr;
+    bool null_tagged = false;        // unsplit layers carry set_nonfluid_cells_nullcollide tags ...
+    uint64_t null_tagged_at = 0;     // ... made at this step count (the tagged lattice alternates with the swaps)
+    unsigned int* d_counters = nullptr;   // scratch words for the geometry kernels
+
     double* d_rho = nullptr;       // persistent read-out staging
     double* d_u = nullptr;
     bool first = true;         // boundary cells hold host-visible (stored) values
@@ -117,12 +132,23 @@ struct lbm_b200 {
 
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // device->host copies of the split read-out
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    static constexpr int READOUT_CHUNKS = 8;
+    cudaEvent_t ev_chunk[READOUT_CHUNKS] = {};
+    cudaEvent_t ev_copied = nullptr;
+    bool readout_pending = false;
     bool timed = false;
     uint64_t steps = 0;
     uint64_t full_halo_at = ~0ull;   // time level for which neighbours pushed their full edge planes
     uint64_t launches = 0;
     bool edges_done = false;   // split-phase state
+
+    // CUDA graphs of step runs (graph_mode: 1 always, 0 never, -1 automatic)
+    int graph_mode = -1;
+    static constexpr int GRAPH_STEPS = 16;          // steps per graph (even: the buffer index returns)
+    cudaGraphExec_t graph[2] = { nullptr, nullptr };   // [cur at entry]
+    uint64_t graph_launches = 0;                    // kernel launches inside one graph
 
     // direct peer stores: [side]
     double* peer_f[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   // [side][buffer]
@@ -131,19 +157,25 @@ struct lbm_b200 {
     void* peer_ipc_base[2] = { nullptr, nullptr };
     cudaIpcMemHandle_t peer_ipc_handle[2] = {};
     bool peer_ipc_shared = false;                   // both sides map the same exporter (ring of two)
-    unsigned long long* d_flags = nullptr;          // [side]: sweeps completed by the neighbour on that side
+    unsigned long long* d_flags = nullptr;          // [0],[1]: sweeps completed by the neighbour on that side,
+                                                    // [2]: sweeps completed by this slab (the epoch), [4]: scratch
     unsigned long long* peer_flag[2] = { nullptr, nullptr };   // the neighbour's counter for us
-    unsigned long long halo_epoch = 0;              // sweeps completed since the peers were connected
     int* d_halo_error = nullptr;
+    int* h_halo_error = nullptr;                    // pinned, mapped: set by the wait kernel on a time-out
+    int* h_halo_error_dev = nullptr;                // its device address
     int clock_khz = 1965000;
+    int sweep_mode = -1;                            // SWEEP_* for the interior launch; -1: chosen per geometry (LBM_B200_SWEEP_MODE)
     long long pull_offset[27] = {};                 // c_z*plane + c_y*P + c_x per direction
     unsigned long long* d_trace = nullptr;         // LBM_B200_HALO_TRACE=<file prefix>: wait-kernel timestamps
     static constexpr int TRACE_EPOCHS = 8192;
-    int* h_halo_error = nullptr;                    // pinned mirror
 
     size_t ncell() const { return (size_t) (g.xl + 2) * (g.yl + 2) * (g.zl + 2); }
     size_t field_bytes() const { return (size_t) g.qstride * Q * sizeof(double); }
     size_t map_elems() const { return (size_t) g.qstride; }
+    size_t bits_words() const { return map_elems() / 32 + 2; }
+    bool lo_interface() const { return z_first != 1; }
+    bool hi_interface() const { return z_first + g.zl - 1 != zl_global; }
+    bool is_slab() const { return g.zl != zl_global; }
 };
 
 namespace {
@@ -187,157 +219,244 @@ int fill_weights(lbm_b200* h, int buffer)
     return 0;
 }
 
-// Checks the dense host maps (optionally copying them from caller arrays in the same parallel pass):
-// known kinds, bc ids inside the table and of the same kind, PERIODIC only on the ghost shell.
-int validate_maps(lbm_b200* h, const uint8_t* kind_src, const uint16_t* bcid_src)
+void drop_graphs(lbm_b200* h)
 {
-    const Layout& g = h->g;
-    const int nb = (int) h->h_bc.size();
-    const size_t rows = (size_t) (g.zl + 2) * (g.yl + 2);
-    int bad = 0;
-    long long bad_at = -1;
-    #pragma omp parallel for schedule(static)
-    for (long long r = 0; r < (long long) rows; ++r) {
-        const int z = (int) (r / (g.yl + 2)), y = (int) (r % (g.yl + 2));
-        const size_t row = (size_t) r * (g.xl + 2);
-        if (kind_src) memcpy(&h->h_kind[row], kind_src + row, (size_t) g.xl + 2);
-        if (kind_src && bcid_src) memcpy(&h->h_bcid[row], bcid_src + row, ((size_t) g.xl + 2) * sizeof(uint16_t));
-        if (kind_src && !bcid_src) memset(&h->h_bcid[row], 0, ((size_t) g.xl + 2) * sizeof(uint16_t));
-        for (int x = 0; x < g.xl + 2; ++x) {
-            const int k = h->h_kind[row + x];
-            int why = 0;
-            if (k >= K_COUNT) why = 1;
-            else if (k >= K_NOSLIP && k <= K_PRESSURE) {
-                const int id = h->h_bcid[row + x];
-                if (id >= nb) why = 2;
-                else if (h->h_bc[id].kind != k) why = 3;
-            } else if (k == K_PERIODIC && x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1) why = 4;
-            if (why) {
-                #pragma omp critical
-                if (!bad) { bad = why; bad_at = (long long) (row + x); }
-            }
-        }
+    for (int i = 0; i < 2; ++i) {
+        if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
+        h->graph[i] = nullptr;
     }
-    if (bad) {
-        const long long x = bad_at % (g.xl + 2), y = (bad_at / (g.xl + 2)) % (g.yl + 2), z = bad_at / ((long long) (g.xl + 2) * (g.yl + 2));
-        const char* msg[] = { "", "unknown kind", "bc id outside the table", "kind differs from table[bc id].kind", "PERIODIC is a ghost-shell kind" };
-        return fail(LBM_B200_EINVAL, "cell (%lld,%lld,%lld): %s", x, y, z, msg[bad]);
+}
+
+void mark_geometry_dirty(lbm_b200* h)
+{
+    h->geom_dirty = true;
+    h->materialized = false;
+    drop_graphs(h);
+}
+
+// ---- the handler table ---------------------------------------------------------------------------
+int sync_table(lbm_b200* h)
+{
+    const size_t n = std::max<size_t>(1, h->h_bc.size());
+    std::vector<BcRec> recs(n);
+    memset(recs.data(), 0, recs.size() * sizeof(BcRec));
+    for (size_t i = 0; i < h->h_bc.size(); ++i) {
+        recs[i].kind = h->h_bc[i].kind;
+        for (int d = 0; d < 3; ++d) recs[i].v[d] = h->h_bc[i].v[d];
+        recs[i].rho = h->h_bc[i].rho;
+        if (recs[i].kind == LBM_B200_INFLOW) feq_host(h->Q, recs[i].rho, recs[i].v, recs[i].feq);
+    }
+    if ((int) n > h->d_bc_cap) {
+        // kernels in flight may still read the old table
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->d_bc) CU(cudaFree(h->d_bc));
+        h->d_bc = nullptr;
+        const size_t cap = std::max<size_t>(64, 2 * n);
+        CU(cudaMalloc(&h->d_bc, cap * sizeof(BcRec)));
+        h->d_bc_cap = (int) cap;
+    }
+    CU(cudaMemcpyAsync(h->d_bc, recs.data(), n * sizeof(BcRec), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // recs goes out of scope
+    drop_graphs(h);
+    return 0;
+}
+
+bool known_kind(int k) { return k >= K_FLUID && k < K_COUNT; }
+
+int check_table(const lbm_b200_bc* table, int n)
+{
+    if (n < 0 || n > 65535 || (n > 0 && !table)) return fail(LBM_B200_EINVAL, "bad handler table");
+    for (int i = 0; i < n; ++i)
+        if (!known_kind(table[i].kind)) return fail(LBM_B200_EINVAL, "handler %d: unknown kind %d", i, table[i].kind);
+    return 0;
+}
+
+// ---- layers ----------------------------------------------------------------------------------------
+int alloc_layer_maps(lbm_b200* h, GeoLayer& L)
+{
+    CU(cudaMalloc(&L.kind, h->map_elems()));
+    CU(cudaMalloc(&L.bcid, h->map_elems() * sizeof(uint16_t)));
+    CU(cudaMalloc(&L.mask, h->map_elems() * sizeof(uint32_t)));
+    CU(cudaMalloc(&L.bits, h->bits_words() * sizeof(uint32_t)));
+    return 0;
+}
+
+void free_layer(GeoLayer& L, bool maps)
+{
+    if (maps) {
+        if (L.kind) cudaFree(L.kind);
+        if (L.bcid) cudaFree(L.bcid);
+        if (L.mask) cudaFree(L.mask);
+        if (L.bits) cudaFree(L.bits);
+    }
+    if (L.inplace) cudaFree(L.inplace);
+    if (L.wall) cudaFree(L.wall);
+    L = GeoLayer();
+}
+
+// the two lattices start to carry different handlers
+int ensure_split(lbm_b200* h)
+{
+    if (h->split) return 0;
+    if (h->is_slab())
+        return fail(LBM_B200_ESTATE, "handlers that differ between the two lattices (literal edits) are limited to whole domains, not slabs");
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->layer[1].inplace && h->layer[1].inplace != h->layer[0].inplace) cudaFree(h->layer[1].inplace);
+    h->layer[1] = GeoLayer();
+    TRY(alloc_layer_maps(h, h->layer[1]));
+    CU(cudaMemcpyAsync(h->layer[1].kind, h->layer[0].kind, h->map_elems(), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->layer[1].bcid, h->layer[0].bcid, h->map_elems() * sizeof(uint16_t), cudaMemcpyDeviceToDevice, h->stream));
+    h->split = true;
+    if (h->null_tagged) {
+        // the tags sit in the lattice that was the collide field when they were made
+        const int tagged = ((h->steps - h->null_tagged_at) & 1) ? 1 - h->cur : h->cur;
+        const long long n = (long long) h->map_elems();
+        untag_null_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, h->stream>>>(h->layer[1 - tagged].kind, h->layer[1 - tagged].bcid,
+                                                                              h->d_bc, (int) h->h_bc.size(), n);
+        h->launches++;
+        CU(cudaGetLastError());
+        h->null_tagged = false;
+    }
+    mark_geometry_dirty(h);
+    return 0;
+}
+
+// both lattices carry the same handlers again (set_geometry replaces everything)
+void unsplit(lbm_b200* h)
+{
+    if (!h->split) return;
+    cudaStreamSynchronize(h->stream);
+    free_layer(h->layer[1], true);
+    h->layer[1] = h->layer[0];
+    h->split = false;
+}
+
+// which layers an edit touches: both lattices, or (literal) the collide field's only
+struct LayerSel {
+    GeoLayer* l[2];
+    int n;
+};
+int select_layers(lbm_b200* h, int literal, LayerSel* sel)
+{
+    if (literal) {
+        TRY(ensure_split(h));
+        sel->l[0] = &h->layer[h->cur];
+        sel->n = 1;
+    } else {
+        sel->l[0] = &h->layer[0];
+        sel->l[1] = &h->layer[1];
+        sel->n = h->split ? 2 : 1;
     }
     return 0;
 }
 
-// upload maps, boundary table, link mask, ghost-fluid list
+// builds link mask / bit map of the steps src -> dst and the list of cells collided in place in dst
+int build_step_maps(lbm_b200* h, int src, int dst, bool* periodic_z)
+{
+    const Layout& g = h->g;
+    GeoLayer& S = h->layer[src];
+    GeoLayer& D = h->layer[dst];
+    CU(cudaMemsetAsync(S.mask, 0x80, h->map_elems() * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(S.bits, 0, h->bits_words() * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned int), h->stream));
+    const int lo = h->lo_interface(), hi = h->hi_interface();
+    dispatch_q(h->Q, [&](auto Qc) {
+        build_mask_kernel<decltype(Qc)::value><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(S.kind, D.kind, S.mask, S.bits, g, lo, hi, h->d_counters);
+        return 0;
+    });
+    h->launches++;
+    CU(cudaGetLastError());
+    unsigned int c[4];
+    CU(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (c[1] & 1u) *periodic_z = true;
+    if (D.inplace) CU(cudaFree(D.inplace));
+    D.inplace = nullptr;
+    D.n_inplace = (int) c[0];
+    if (D.n_inplace) {
+        CU(cudaMalloc(&D.inplace, (size_t) D.n_inplace * sizeof(int)));
+        collect_inplace_kernel<<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(S.kind, D.kind, g, lo, hi, D.inplace, c[0], h->d_counters + 2);
+        h->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    // the sorted list of streamed cells next to a wall: count per x-row, prefix sum, fill
+    if (S.wall) CU(cudaFree(S.wall));
+    S.wall = nullptr;
+    S.n_wall = S.wall_lo = S.wall_hi = 0;
+    S.flagged = (double) c[3] / ((double) g.xl * g.yl * g.zl);
+    const int rows = g.yl * g.zl;
+    DevBuf counts;
+    CU(cudaMalloc(&counts.p, (size_t) rows * sizeof(int)));
+    const int warps_per_block = 4;
+    const int row_blocks = (rows + warps_per_block - 1) / warps_per_block;
+    wall_count_kernel<<<row_blocks, 32 * warps_per_block, 0, h->stream>>>(S.mask, g, counts.as<int>());
+    h->launches++;
+    CU(cudaGetLastError());
+    std::vector<int> start(rows);
+    CU(cudaMemcpyAsync(start.data(), counts.p, (size_t) rows * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    long long total = 0;
+    for (int r = 0; r < rows; ++r) {
+        const int n = start[r];
+        start[r] = (int) total;
+        total += n;
+        if (r == g.yl - 1) S.wall_lo = (int) total;
+    }
+    S.wall_hi = (int) (total - (g.zl > 1 ? start[(size_t) (g.zl - 1) * g.yl] : 0));
+    S.n_wall = (int) total;
+    if (S.n_wall) {
+        CU(cudaMalloc(&S.wall, (size_t) S.n_wall * sizeof(int)));
+        CU(cudaMemcpyAsync(counts.p, start.data(), (size_t) rows * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        wall_fill_kernel<<<row_blocks, 32 * warps_per_block, 0, h->stream>>>(S.mask, g, counts.as<int>(), S.wall);
+        h->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+// link masks, in-place lists, periodic-z bookkeeping
 int commit_geometry(lbm_b200* h)
 {
     if (!h->geom_dirty) return 0;
     const Layout& g = h->g;
-    const size_t n = h->ncell();
-    // boundary records
-    {
-        std::vector<BcRec> recs(std::max<size_t>(1, h->h_bc.size()));
-        memset(recs.data(), 0, recs.size() * sizeof(BcRec));
-        for (size_t i = 0; i < h->h_bc.size(); ++i) {
-            recs[i].kind = h->h_bc[i].kind;
-            for (int d = 0; d < 3; ++d) recs[i].v[d] = h->h_bc[i].v[d];
-            recs[i].rho = h->h_bc[i].rho;
-            if (recs[i].kind == LBM_B200_INFLOW) feq_host(h->Q, recs[i].rho, recs[i].v, recs[i].feq);
-        }
-        if (h->d_bc) CU(cudaFree(h->d_bc));
-        h->d_bc = nullptr;
-        CU(cudaMalloc(&h->d_bc, recs.size() * sizeof(BcRec)));
-        CU(cudaMemcpyAsync(h->d_bc, recs.data(), recs.size() * sizeof(BcRec), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-    }
-    if (h->geom_unchecked) {
-        TRY(validate_maps(h, nullptr, nullptr));
-        h->geom_unchecked = false;
-    }
-    // ghost-shell cells that kept the fluid handler, and periodic z: only the shell is scanned
-    std::vector<int> ghost;
     bool periodic_z = false;
-    const bool z_lo_shell = h->z_first == 1, z_hi_shell = h->z_first + g.zl - 1 == h->zl_global;
-    auto visit = [&](int x, int y, int z) {
-        const int k = h->h_kind[((size_t) z * (g.yl + 2) + y) * (g.xl + 2) + x];
-        if (k == K_FLUID) ghost.push_back(cell_at(g, x, y, z));
-        if (k == K_PERIODIC && (z == 0 || z == g.zl + 1)) periodic_z = true;
-    };
-    for (int z = 0; z < g.zl + 2; ++z) {
-        const bool zshell = (z == 0 && z_lo_shell) || (z == g.zl + 1 && z_hi_shell);
-        if ((z == 0 || z == g.zl + 1) && !zshell) continue;   // interface ghost plane: the neighbour's cells
-        for (int y = 0; y < g.yl + 2; ++y) {
-            if (zshell || y == 0 || y == g.yl + 1) {
-                for (int x = 0; x < g.xl + 2; ++x) visit(x, y, z);
-            } else {
-                visit(0, y, z);
-                visit(g.xl + 1, y, z);
-            }
-        }
+    if (h->split) {
+        TRY(build_step_maps(h, 0, 1, &periodic_z));
+        TRY(build_step_maps(h, 1, 0, &periodic_z));
+    } else {
+        if (h->layer[1].inplace && h->layer[1].inplace != h->layer[0].inplace) cudaFree(h->layer[1].inplace);
+        h->layer[1] = h->layer[0];
+        h->layer[1].inplace = nullptr;
+        TRY(build_step_maps(h, 0, 0, &periodic_z));
+        h->layer[1] = h->layer[0];
     }
     h->ring_lo = h->ring_hi = false;
-    if (periodic_z && (h->z_first != 1 || g.zl != h->zl_global)) {
+    if (periodic_z && h->is_slab()) {
         // closed by a ring of slabs instead: the first and the last slab must be each other's neighbours
         h->ring_lo = h->z_first == 1;
         h->ring_hi = h->z_first + g.zl - 1 == h->zl_global;
         periodic_z = false;
     }
     h->wrap_z = periodic_z ? 1 : 0;
-    if (!ghost.empty() && g.zl != h->zl_global)
-        return fail(LBM_B200_EINVAL, "%zu ghost-shell cells carry the fluid handler; on a multi-slab domain the "
-                    "whole shell must be covered by boundary conditions", ghost.size());
-
-    // dense -> padded maps through a device staging copy
-    {
-        DevBuf buf8, buf16;          // own the staging for the duration of this block either way
-        buf8.p = h->stage_kind;
-        buf16.p = h->stage_bcid;
-        h->stage_kind = nullptr;
-        h->stage_bcid = nullptr;
-        if (!buf8.p || !buf16.p) {   // maps edited on the host (boxes, mask): upload the host copies
-            if (buf8.p) { cudaFree(buf8.p); buf8.p = nullptr; }
-            if (buf16.p) { cudaFree(buf16.p); buf16.p = nullptr; }
-            CU(cudaMalloc(&buf8.p, n));
-            CU(cudaMalloc(&buf16.p, n * sizeof(uint16_t)));
-            CU(cudaMemcpyAsync(buf8.p, h->h_kind.data(), n, cudaMemcpyHostToDevice, h->stream));
-            CU(cudaMemcpyAsync(buf16.p, h->h_bcid.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
-        }
-        uint8_t* stage8 = buf8.as<uint8_t>();
-        uint16_t* stage16 = buf16.as<uint16_t>();
-        CU(cudaMemsetAsync(h->d_kind, K_NULL, h->map_elems(), h->stream));
-        CU(cudaMemsetAsync(h->d_bcid, 0, h->map_elems() * sizeof(uint16_t), h->stream));
-        scatter_map_kernel<uint8_t><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(stage8, h->d_kind, g, 0);
-        scatter_map_kernel<uint16_t><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(stage16, h->d_bcid, g, 0);
-        CU(cudaMemsetAsync(h->d_mask, 0x80, h->map_elems() * sizeof(uint32_t), h->stream));
-        CU(cudaMemsetAsync(h->d_bits, 0, (h->map_elems() / 32 + 2) * sizeof(uint32_t), h->stream));
-        dispatch_q(h->Q, [&](auto Qc) {
-            build_mask_kernel<decltype(Qc)::value><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->d_kind, h->d_mask, h->d_bits, g);
-            return 0;
-        });
-        h->launches += 3;
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(h->stream));
-    }
-    if (h->d_ghost) CU(cudaFree(h->d_ghost));
-    h->d_ghost = nullptr;
-    h->n_ghost = (int) ghost.size();
-    if (h->n_ghost) {
-        CU(cudaMalloc(&h->d_ghost, ghost.size() * sizeof(int)));
-        CU(cudaMemcpy(h->d_ghost, ghost.data(), ghost.size() * sizeof(int), cudaMemcpyHostToDevice));
-    }
+    if (h->layer[0].n_inplace && h->is_slab())
+        return fail(LBM_B200_EINVAL, "%d ghost-shell cells carry the fluid handler; on a multi-slab domain the "
+                    "whole shell must be covered by boundary conditions", h->layer[0].n_inplace);
     h->geom_dirty = false;
     return 0;
 }
 
-int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step = 1)
+void fill_sweep_params(lbm_b200* h, SweepParams& p, int z0, bool with_peers, int z_step, int* grid_xy)
 {
-    if (nz <= 0) return 0;
     const Layout& g = h->g;
-    SweepParams p{};
+    const GeoLayer& S = h->layer[h->cur];
     p.src = h->f[h->cur];
     p.dst = h->f[1 - h->cur];
-    p.mask = h->d_mask;
-    p.bits = h->d_bits;
-    p.kind = h->d_kind;
-    p.bcid = h->d_bcid;
+    p.mask = S.mask;
+    p.bits = S.bits;
+    p.kind = S.kind;
+    p.bcid = S.bcid;
     p.bc = h->d_bc;
     p.g = g;
     p.z0 = z0;
@@ -365,11 +484,27 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step = 1)
         p.dstq[q] = p.dst + (long long) q * g.qstride;
     }
     const int bx = 1 << shift, by = LBM_SWEEP_THREADS >> shift;
-    dim3 grid((g.xl + bx - 1) / bx, (g.yl + by - 1) / by, nz);
+    grid_xy[0] = (g.xl + bx - 1) / bx;
+    grid_xy[1] = (g.yl + by - 1) / by;
+}
+
+int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step, int mode)
+{
+    if (nz <= 0) return 0;
+    SweepParams p{};
+    int gxy[2];
+    fill_sweep_params(h, p, z0, with_peers, z_step, gxy);
+    dim3 grid(gxy[0], gxy[1], nz);
     dispatch_q(h->Q, [&](auto Qc) {
         constexpr int Q = decltype(Qc)::value;
-        if (h->exact) sweep_kernel<Q, true><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
-        else sweep_kernel<Q, false><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+        auto go = [&](auto Ex) {
+            constexpr bool EX = decltype(Ex)::value;
+            if (mode == SWEEP_BULK) sweep_kernel<Q, EX, SWEEP_BULK><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+            else if (mode == SWEEP_CHECKED) sweep_kernel<Q, EX, SWEEP_CHECKED><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+            else sweep_kernel<Q, EX, SWEEP_INLINE><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+        };
+        if (h->exact) go(std::true_type{});
+        else go(std::false_type{});
         return 0;
     });
     h->launches++;
@@ -377,15 +512,58 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step = 1)
     return 0;
 }
 
-int launch_ghost(lbm_b200* h)
+// wall cells [begin, end) of the source layer's sorted list
+int launch_wall(lbm_b200* h, int begin, int end, bool with_peers)
 {
-    if (!h->n_ghost) return 0;
+    if (end <= begin) return 0;
+    SweepParams p{};
+    int gxy[2];
+    fill_sweep_params(h, p, 1, with_peers, 1, gxy);
+    const GeoLayer& S = h->layer[h->cur];
+    const int n = end - begin;
+    dispatch_q(h->Q, [&](auto Qc) {
+        constexpr int Q = decltype(Qc)::value;
+        if (h->exact) wall_kernel<Q, true><<<(n + 127) / 128, 128, 0, h->stream>>>(p, S.wall + begin, n);
+        else wall_kernel<Q, false><<<(n + 127) / 128, 128, 0, h->stream>>>(p, S.wall + begin, n);
+        return 0;
+    });
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// how the interior launch treats flagged cells for the current source layer
+int interior_mode(const lbm_b200* h)
+{
+    if (h->sweep_mode >= 0) return h->sweep_mode;
+    // large solid regions: look at the bit before pulling (see SWEEP_CHECKED)
+    return h->layer[h->cur].flagged > 0.10 ? SWEEP_CHECKED : SWEEP_BULK;
+}
+
+// planes [z0, z0 + nz) in full: the sweep plus, unless it handles them inline, the wall cells of those planes
+int sweep_planes(lbm_b200* h, int z0, int nz, bool with_peers)
+{
+    if (nz <= 0) return 0;
+    const int mode = interior_mode(h);
+    TRY(launch_sweep(h, z0, nz, with_peers, 1, mode));
+    if (mode == SWEEP_INLINE) return 0;
+    const GeoLayer& S = h->layer[h->cur];
+    const int begin = z0 > 1 ? S.wall_lo : 0;
+    const int end = z0 + nz - 1 < h->g.zl ? S.n_wall - S.wall_hi : S.n_wall;
+    return launch_wall(h, begin, end, with_peers);
+}
+
+// cells that are collided without being streamed (K1g), in the buffer that becomes the collide field
+int launch_inplace(lbm_b200* h)
+{
+    const GeoLayer& D = h->layer[1 - h->cur];
+    if (!D.n_inplace) return 0;
     double* field = h->f[1 - h->cur];
     dispatch_q(h->Q, [&](auto Qc) {
         constexpr int Q = decltype(Qc)::value;
-        const int blocks = (h->n_ghost + 127) / 128;
-        if (h->exact) ghost_fluid_kernel<Q, true><<<blocks, 128, 0, h->stream>>>(field, h->g.qstride, h->d_ghost, h->n_ghost, h->tau, 1.0 / h->tau);
-        else ghost_fluid_kernel<Q, false><<<blocks, 128, 0, h->stream>>>(field, h->g.qstride, h->d_ghost, h->n_ghost, h->tau, 1.0 / h->tau);
+        const int blocks = (D.n_inplace + 127) / 128;
+        if (h->exact) ghost_fluid_kernel<Q, true><<<blocks, 128, 0, h->stream>>>(field, h->g.qstride, D.inplace, D.n_inplace, h->tau, 1.0 / h->tau);
+        else ghost_fluid_kernel<Q, false><<<blocks, 128, 0, h->stream>>>(field, h->g.qstride, D.inplace, D.n_inplace, h->tau, 1.0 / h->tau);
         return 0;
     });
     h->launches++;
@@ -401,11 +579,12 @@ int halo_wait(lbm_b200* h)
     if (!has_peers(h)) return 0;
     // (the clock rate is read once at creation: cudaDeviceGetAttribute(cudaDevAttrClockRate) is a
     //  driver round trip of milliseconds and made the host the bottleneck when it ran every step)
-    const long long timeout = (long long) h->clock_khz * 1000 * 20;    // ~20 s
+    static const long long timeout_ms = [] { const char* e = getenv("LBM_B200_HALO_TIMEOUT_MS"); return e ? std::max(1LL, atoll(e)) : 20000LL; }();
+    const long long timeout = (long long) h->clock_khz * timeout_ms;   // cycles; default ~20 s
     halo_wait_kernel<<<1, 1, 0, h->stream>>>(h->peer_flag[LBM_B200_DOWN] ? h->d_flags + LBM_B200_DOWN : nullptr,
                                              h->peer_flag[LBM_B200_UP] ? h->d_flags + LBM_B200_UP : nullptr,
-                                             h->halo_epoch, timeout, h->d_halo_error,
-                                             h->halo_epoch < lbm_b200::TRACE_EPOCHS ? h->d_trace : nullptr);
+                                             h->d_flags + 2, timeout, h->d_halo_error, h->h_halo_error_dev,
+                                             h->d_trace, lbm_b200::TRACE_EPOCHS);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -413,19 +592,28 @@ int halo_wait(lbm_b200* h)
 int halo_signal(lbm_b200* h)
 {
     if (!has_peers(h)) return 0;
-    h->halo_epoch++;
-    halo_signal_kernel<<<1, 1, 0, h->stream>>>(h->peer_flag[LBM_B200_DOWN], h->peer_flag[LBM_B200_UP], h->halo_epoch, h->d_flags + 4);
+    halo_signal_kernel<<<1, 1, 0, h->stream>>>(h->peer_flag[LBM_B200_DOWN], h->peer_flag[LBM_B200_UP], h->d_flags + 2, h->d_flags + 4);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
 }
+int halo_failed(const lbm_b200* h)
+{
+    if (h->h_halo_error && *(volatile int*) h->h_halo_error)
+        return fail(LBM_B200_ETIMEOUT, "a neighbour slab did not complete its sweep within the hand-shake timeout; "
+                    "the populations of this slab are no longer valid");
+    return 0;
+}
 int halo_check(lbm_b200* h)
 {
-    if (!has_peers(h)) return 0;
+    if (!has_peers(h)) return halo_failed(h);
     int err = 0;
     CU(cudaMemcpyAsync(&err, h->d_halo_error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    if (err) return fail(LBM_B200_ETIMEOUT, "a neighbour slab did not complete its sweep within the hand-shake timeout");
+    if (err) {
+        if (h->h_halo_error) *h->h_halo_error = 1;
+        return halo_failed(h);
+    }
     return 0;
 }
 
@@ -437,19 +625,102 @@ void finish_step(lbm_b200* h)
     h->steps++;
 }
 
+// the launches of one time step on h->stream
+int enqueue_step(lbm_b200* h)
+{
+    if (has_peers(h) && h->g.zl >= 3) {
+        // Only the two edge planes read ghost planes and feed the neighbours, so only they take
+        // part in the hand-shake; the interior sweep that follows gives every neighbour a whole
+        // step of slack before its next wait.
+        TRY(halo_wait(h));
+        TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1, SWEEP_INLINE));
+        TRY(halo_signal(h));
+        TRY(sweep_planes(h, 2, h->g.zl - 2, false));
+    } else {
+        TRY(halo_wait(h));
+        TRY(sweep_planes(h, 1, h->g.zl, true));
+        TRY(halo_signal(h));
+    }
+    TRY(launch_inplace(h));
+    finish_step(h);
+    return 0;
+}
+
+bool graphs_wanted(const lbm_b200* h)
+{
+    if (h->graph_mode >= 0) return h->graph_mode != 0;
+    // automatic: lattices whose sweep lasts a few microseconds, where the launch overhead shows
+    return (size_t) h->g.xl * h->g.yl * h->g.zl <= ((size_t) 1 << 21);
+}
+
+// GRAPH_STEPS steps replayed from one CUDA graph (captured per buffer parity at entry)
+int run_graph(lbm_b200* h)
+{
+    const int parity = h->cur;
+    if (!h->graph[parity]) {
+        const uint64_t launches0 = h->launches, steps0 = h->steps;
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (int s = 0; s < lbm_b200::GRAPH_STEPS && rc == 0; ++s) rc = enqueue_step(h);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        h->graph_launches = h->launches - launches0;
+        h->launches = launches0;      // nothing has run yet
+        h->steps = steps0;
+        if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(LBM_B200_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&h->graph[parity], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(LBM_B200_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    }
+    CU(cudaGraphLaunch(h->graph[parity], h->stream));
+    h->launches += h->graph_launches;
+    h->steps += lbm_b200::GRAPH_STEPS;
+    h->materialized = false;
+    return 0;
+}
+
+// n steps on h->stream (no events, no state checks)
+int enqueue_steps(lbm_b200* h, uint64_t n)
+{
+    while (n > 0) {
+        if (!h->first && n >= (uint64_t) lbm_b200::GRAPH_STEPS && graphs_wanted(h)) {
+            TRY(run_graph(h));
+            n -= lbm_b200::GRAPH_STEPS;
+        } else {
+            TRY(enqueue_step(h));
+            --n;
+        }
+    }
+    return 0;
+}
+
+int ready_to_step(lbm_b200* h)
+{
+    if (h->edges_done) return fail(LBM_B200_ESTATE, "a split-phase step is in flight");
+    TRY(halo_failed(h));
+    TRY(commit_geometry(h));
+    if ((h->ring_lo && !h->peer_f[LBM_B200_DOWN][0]) || (h->ring_hi && !h->peer_f[LBM_B200_UP][0]))
+        return fail(LBM_B200_ESTATE, "periodic z on a multi-slab domain needs the first and last slab connected as a ring "
+                    "(lbm_b200_connect / lbm_b200_connect_local on that side)");
+    return 0;
+}
+
 int materialize(lbm_b200* h)
 {
     TRY(commit_geometry(h));
     if (h->materialized) return 0;
     const Layout& g = h->g;
-    // interface ghost planes count as interior only if the neighbours' full planes were pushed
-    // there for this time level (lbm_b200_halo_push_all); otherwise links across a cut are skipped
-    const int lo_open = h->z_first != 1 && h->full_halo_at == h->steps;
-    const int hi_open = h->z_first + g.zl - 1 != h->zl_global && h->full_halo_at == h->steps;
+    const GeoLayer& L = h->layer[h->cur];
+    // links from our boundary cells into an interface ghost plane can only be evaluated if the neighbours'
+    // full planes were pushed there for this time level (lbm_b200_halo_push_all)
+    const int lo_if = h->lo_interface(), hi_if = h->hi_interface();
+    const int lo_open = lo_if && h->full_halo_at == h->steps;
+    const int hi_open = hi_if && h->full_halo_at == h->steps;
     dispatch_q(h->Q, [&](auto Qc) {
         constexpr int Q = decltype(Qc)::value;
-        if (h->exact) materialize_kernel<Q, true><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, h->d_bcid, h->d_bc, g, lo_open, hi_open);
-        else materialize_kernel<Q, false><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, h->d_bcid, h->d_bc, g, lo_open, hi_open);
+        if (h->exact) materialize_kernel<Q, true><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->f[h->cur], L.kind, L.bcid, h->d_bc, g, lo_if, hi_if, lo_open, hi_open);
+        else materialize_kernel<Q, false><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(h->f[h->cur], L.kind, L.bcid, h->d_bc, g, lo_if, hi_if, lo_open, hi_open);
         return 0;
     });
     h->launches++;
@@ -458,25 +729,79 @@ int materialize(lbm_b200* h)
     return 0;
 }
 
-void drop_staged_maps(lbm_b200* h)
-{
-    if (h->stage_kind) cudaFree(h->stage_kind);
-    if (h->stage_bcid) cudaFree(h->stage_bcid);
-    h->stage_kind = nullptr;
-    h->stage_bcid = nullptr;
-}
-
 // Geometry edits after time steps: first let the boundary cells of the OLD geometry take the values
 // the reference holds (its non-fluid pass ran after every step), then remember that the next stream
 // must pull stored values -- new boundary cells still carry their former fluid populations.
 int before_geometry_change(lbm_b200* h)
 {
-    if (h->steps > 0 && !h->geom_dirty) {
-        DeviceGuard guard(h->device);
-        if (!guard.ok) return fail(LBM_B200_ECUDA, "cannot select CUDA device %d", h->device);
-        TRY(materialize(h));
-    }
+    if (h->steps > 0 && !h->geom_dirty) TRY(materialize(h));
     h->first = true;
+    return 0;
+}
+
+// one inclusive box in GLOBAL indices -> the local cells it covers in the given layers
+int paint_box(lbm_b200* h, const LayerSel& sel, const uint64_t* e, int kind, uint16_t id)
+{
+    const Layout& g = h->g;
+    const long long zoff = h->z_first - 1;   // local z = global z - zoff
+    const long long lz0 = std::max<long long>((long long) e[4] - zoff, 0);
+    const long long lz1 = std::min<long long>((long long) e[5] - zoff, g.zl + 1);
+    if (lz0 > lz1) return 0;
+    const int nx = (int) (e[1] - e[0] + 1), ny = (int) (e[3] - e[2] + 1), nz = (int) (lz1 - lz0 + 1);
+    const int threads = nx >= 128 ? 128 : 32;
+    dim3 grid((nx + threads - 1) / threads, ny, nz);
+    for (int l = 0; l < sel.n; ++l) {
+        paint_box_kernel<<<grid, threads, 0, h->stream>>>(sel.l[l]->kind, sel.l[l]->bcid, g, (int) e[0], (int) e[2], (int) lz0, nx, ny, (uint8_t) kind, id);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int check_box(const lbm_b200* h, const uint64_t* e, int b)
+{
+    const Layout& g = h->g;
+    // the reference asserts these (domain.hpp:180-181)
+    if (!(e[1] >= e[0] && e[3] >= e[2] && e[5] >= e[4])) return fail(LBM_B200_EINVAL, "box %d: end before begin", b);
+    if (!(e[1] < (uint64_t) g.xl + 2 && e[3] < (uint64_t) g.yl + 2 && e[5] < (uint64_t) h->zl_global + 2))
+        return fail(LBM_B200_EINVAL, "box %d: extent outside the domain", b);
+    return 0;
+}
+
+// dense kind / handler-id planes [z_begin, z_begin + z_count) from the host -> checked on the device -> maps
+int upload_map_planes(lbm_b200* h, const uint8_t* kind, const uint16_t* bc_id, int z_begin, int z_count, const LayerSel& sel)
+{
+    const Layout& g = h->g;
+    const size_t n = (size_t) (g.xl + 2) * (g.yl + 2) * z_count;
+    DevBuf b8, b16, bres;
+    CU(cudaMalloc(&b8.p, n));
+    CU(cudaMalloc(&b16.p, n * sizeof(uint16_t)));
+    CU(cudaMalloc(&bres.p, sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(b8.p, kind, n, cudaMemcpyHostToDevice, h->stream));
+    if (bc_id) CU(cudaMemcpyAsync(b16.p, bc_id, n * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    else CU(cudaMemsetAsync(b16.p, 0, n * sizeof(uint16_t), h->stream));
+    CU(cudaMemsetAsync(bres.p, 0xFF, sizeof(unsigned long long), h->stream));
+    validate_dense_kernel<<<map_grid(g, z_count), 128, 0, h->stream>>>(b8.as<uint8_t>(), b16.as<uint16_t>(), h->d_bc, (int) h->h_bc.size(),
+                                                                        g, z_begin, bres.as<unsigned long long>());
+    h->launches++;
+    CU(cudaGetLastError());
+    unsigned long long res = 0;
+    CU(cudaMemcpyAsync(&res, bres.p, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));     // the caller may release its arrays after this call
+    if (res != ~0ull) {                       // nothing has been changed
+        const unsigned long long at = res / 8;
+        const int why = (int) (res % 8);
+        const long long x = at % (g.xl + 2), y = (at / (g.xl + 2)) % (g.yl + 2), z = at / ((unsigned long long) (g.xl + 2) * (g.yl + 2));
+        const char* msg[] = { "", "unknown kind", "bc id outside the table", "kind differs from table[bc id].kind", "PERIODIC is a ghost-shell kind" };
+        return fail(LBM_B200_EINVAL, "cell (%lld,%lld,%lld): %s", x, y, z, msg[why]);
+    }
+    for (int l = 0; l < sel.n; ++l) {
+        scatter_map_kernel<uint8_t><<<map_grid(g, z_count), 128, 0, h->stream>>>(b8.as<uint8_t>(), sel.l[l]->kind, g, z_begin);
+        scatter_map_kernel<uint16_t><<<map_grid(g, z_count), 128, 0, h->stream>>>(b16.as<uint16_t>(), sel.l[l]->bcid, g, z_begin);
+        h->launches += 2;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));     // the staging buffers are released on return
     return 0;
 }
 
@@ -516,6 +841,8 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
     h->zl_global = (int) zl_global;
     h->z_first = (int) z_first;
     h->tau = tau;
+    if (const char* e = getenv("LBM_B200_GRAPHS")) h->graph_mode = atoi(e);
+    if (const char* e = getenv("LBM_B200_SWEEP_MODE")) h->sweep_mode = std::max(-1, std::min(2, atoi(e)));
     {
         double vel[27 * 3];
         lbm_b200_model(Q, vel, nullptr);
@@ -532,31 +859,48 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
         cudaGetLastError(); return bail(e_ == cudaErrorMemoryAllocation ? LBM_B200_ENOMEM : LBM_B200_ECUDA); } } while (0)
     CUB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    CUB(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CUB(cudaEventCreate(&h->ev_a));
     CUB(cudaEventCreate(&h->ev_b));
+    for (auto& e : h->ev_chunk) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
     // one allocation for both lattices: a neighbour maps it with a single IPC handle
     // (IPC handles address whole allocations, so the hand-shake counters live in its tail)
     CUB(cudaMalloc(&h->f[0], 2 * h->field_bytes() + 256));
     h->f[1] = h->f[0] + (size_t) h->g.qstride * Q;
     h->d_flags = reinterpret_cast<unsigned long long*>(h->f[0] + 2 * (size_t) h->g.qstride * Q);
     CUB(cudaMemset(h->d_flags, 0, 256));
-    CUB(cudaMalloc(&h->d_mask, h->map_elems() * sizeof(uint32_t)));
-    CUB(cudaMalloc(&h->d_bits, (h->map_elems() / 32 + 2) * sizeof(uint32_t)));
-    CUB(cudaMalloc(&h->d_kind, h->map_elems()));
-    CUB(cudaMalloc(&h->d_bcid, h->map_elems() * sizeof(uint16_t)));
+    if (alloc_layer_maps(h, h->layer[0]) != 0) return bail(LBM_B200_ENOMEM);
+    h->layer[1] = h->layer[0];
+    CUB(cudaMalloc(&h->d_counters, 16 * sizeof(unsigned int)));
     if (cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device) != cudaSuccess || h->clock_khz <= 0) {
         cudaGetLastError();
         h->clock_khz = 1965000;
     }
     CUB(cudaMalloc(&h->d_halo_error, sizeof(int)));
     CUB(cudaMemset(h->d_halo_error, 0, sizeof(int)));
+    CUB(cudaHostAlloc(&h->h_halo_error, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *h->h_halo_error = 0;
+    CUB(cudaHostGetDevicePointer(&h->h_halo_error_dev, h->h_halo_error, 0));
     if (getenv("LBM_B200_HALO_TRACE")) {
         CUB(cudaMalloc(&h->d_trace, 2 * lbm_b200::TRACE_EPOCHS * sizeof(unsigned long long)));
         CUB(cudaMemset(h->d_trace, 0, 2 * lbm_b200::TRACE_EPOCHS * sizeof(unsigned long long)));
     }
+    // every cell -- ghost shell included -- starts with the fluid handler (domain.hpp:87-93); the padding
+    // between rows is NULL so that nothing ever treats it as a cell
+    CUB(cudaMemsetAsync(h->layer[0].kind, K_NULL, h->map_elems(), h->stream));
+    CUB(cudaMemsetAsync(h->layer[0].bcid, 0, h->map_elems() * sizeof(uint16_t), h->stream));
 #undef CUB
-    h->h_kind.assign(h->ncell(), (uint8_t) LBM_B200_FLUID);   // domain.hpp:87-93
-    h->h_bcid.assign(h->ncell(), 0);
+    {
+        const uint64_t whole[6] = { 0, xl + 1, 0, yl + 1, 0, zl_global + 1 };
+        LayerSel sel{ { &h->layer[0], nullptr }, 1 };
+        if (paint_box(h, sel, whole, K_FLUID, 0) != 0) return bail(LBM_B200_ECUDA);
+    }
+    lbm_b200_bc fluid{};
+    fluid.kind = LBM_B200_FLUID;
+    fluid.rho = 1.0;
+    h->h_bc.assign(1, fluid);      // id 0: the fluid operator (cells of a fresh domain refer to it)
+    if (sync_table(h) != 0) return bail(LBM_B200_ECUDA);
     if (fill_weights(h, 0) != 0 || fill_weights(h, 1) != 0) return bail(LBM_B200_ECUDA);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { fail(LBM_B200_ECUDA, "initial fill failed"); return bail(LBM_B200_ECUDA); }
     return 0;
@@ -612,38 +956,45 @@ int lbm_b200_destroy(lbm_b200_t* h)
 {
     if (!h) return 0;
     DeviceGuard guard(h->device);
+    if (h->readout_pending && h->ev_copied) cudaEventSynchronize(h->ev_copied);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     if (h->d_trace) {   // diagnostic dump: "<prefix>.<device>.z<first plane>" with entry/exit ns per epoch
         std::vector<unsigned long long> t(2 * lbm_b200::TRACE_EPOCHS);
         cudaDeviceSynchronize();
+        unsigned long long epochs = 0;
+        cudaMemcpy(&epochs, h->d_flags + 2, sizeof epochs, cudaMemcpyDeviceToHost);
         if (cudaMemcpy(t.data(), h->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
             const std::string path = std::string(getenv("LBM_B200_HALO_TRACE") ? getenv("LBM_B200_HALO_TRACE") : "halo_trace")
                     + "." + std::to_string(h->device) + ".z" + std::to_string(h->z_first);
             if (FILE* fp = fopen(path.c_str(), "w")) {
-                for (unsigned long long e = 0; e < h->halo_epoch && e < (unsigned long long) lbm_b200::TRACE_EPOCHS; ++e)
+                for (unsigned long long e = 0; e < epochs && e < (unsigned long long) lbm_b200::TRACE_EPOCHS; ++e)
                     fprintf(fp, "%llu %llu %llu\n", e, t[2 * e], t[2 * e + 1]);
                 fclose(fp);
             }
         }
         cudaFree(h->d_trace);
     }
+    drop_graphs(h);
     if (h->peer_ipc_shared) h->peer_ipc_base[1] = nullptr;
     for (int s = 0; s < 2; ++s) {
         if (h->peer_ipc_base[s]) cudaIpcCloseMemHandle(h->peer_ipc_base[s]);
     }
     if (h->d_halo_error) cudaFree(h->d_halo_error);
+    if (h->h_halo_error) cudaFreeHost(h->h_halo_error);
     if (h->f[0]) cudaFree(h->f[0]);
-    if (h->d_mask) cudaFree(h->d_mask);
-    if (h->d_bits) cudaFree(h->d_bits);
-    if (h->d_kind) cudaFree(h->d_kind);
-    if (h->d_bcid) cudaFree(h->d_bcid);
+    if (h->layer[1].inplace && h->layer[1].inplace != h->layer[0].inplace) cudaFree(h->layer[1].inplace);
+    h->layer[1].inplace = nullptr;
+    if (h->split) free_layer(h->layer[1], true);
+    free_layer(h->layer[0], true);
     if (h->d_bc) cudaFree(h->d_bc);
-    if (h->d_ghost) cudaFree(h->d_ghost);
-    drop_staged_maps(h);
+    if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_rho) cudaFree(h->d_rho);
     if (h->d_u) cudaFree(h->d_u);
     if (h->ev_a) cudaEventDestroy(h->ev_a);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
+    for (auto& e : h->ev_chunk) if (e) cudaEventDestroy(e);
+    if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaGetLastError();
     delete h;
@@ -655,6 +1006,7 @@ int lbm_b200_set_arithmetic(lbm_b200_t* h, int mode)
     if (!h) return fail(LBM_B200_EINVAL, "null handle");
     if (mode != LBM_B200_FAST && mode != LBM_B200_EXACT) return fail(LBM_B200_EINVAL, "unknown arithmetic mode %d", mode);
     h->exact = mode == LBM_B200_EXACT;
+    drop_graphs(h);
     return 0;
 }
 int lbm_b200_set_tau(lbm_b200_t* h, double tau)
@@ -662,6 +1014,13 @@ int lbm_b200_set_tau(lbm_b200_t* h, double tau)
     if (!h) return fail(LBM_B200_EINVAL, "null handle");
     if (!(tau > 0.0)) return fail(LBM_B200_EINVAL, "tau must be positive (got %g)", tau);
     h->tau = tau;
+    drop_graphs(h);
+    return 0;
+}
+int lbm_b200_set_graphs(lbm_b200_t* h, int mode)
+{
+    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    h->graph_mode = mode < 0 ? -1 : (mode ? 1 : 0);
     return 0;
 }
 int lbm_b200_set_stream(lbm_b200_t* h, void* cuda_stream)
@@ -672,107 +1031,212 @@ int lbm_b200_set_stream(lbm_b200_t* h, void* cuda_stream)
     return 0;
 }
 
-int lbm_b200_set_geometry(lbm_b200_t* h, const uint8_t* kind, const uint16_t* bc_id, const lbm_b200_bc* table, int n_table)
+int lbm_b200_set_handlers(lbm_b200_t* h, const lbm_b200_bc* table, int n_table)
 {
     GUARD(h);
-    if (!kind) return fail(LBM_B200_EINVAL, "kind map is null");
-    if (n_table < 0 || n_table > 65535 || (n_table > 0 && !table)) return fail(LBM_B200_EINVAL, "bad boundary table");
-    if (!bc_id && n_table > 1) return fail(LBM_B200_EINVAL, "bc_id map required for a table of %d handlers", n_table);
-    TRY(before_geometry_change(h));
-    const size_t n = h->ncell();
-    // the caller's arrays go to the device straight away (fast when they are pinned) while the host
-    // copies are taken and validated in parallel; commit_geometry() later only scatters them
-    drop_staged_maps(h);
-    CU(cudaMalloc(&h->stage_kind, n));
-    CU(cudaMalloc(&h->stage_bcid, n * sizeof(uint16_t)));
-    CU(cudaMemcpyAsync(h->stage_kind, kind, n, cudaMemcpyHostToDevice, h->stream));
-    if (bc_id) CU(cudaMemcpyAsync(h->stage_bcid, bc_id, n * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
-    else CU(cudaMemsetAsync(h->stage_bcid, 0, n * sizeof(uint16_t), h->stream));
+    TRY(check_table(table, n_table));
+    for (size_t i = 0; i < h->h_bc.size() && i < (size_t) n_table; ++i)
+        if (h->h_bc[i].kind != table[i].kind)
+            return fail(LBM_B200_EINVAL, "handler %zu changes its kind (%d -> %d): a new table must extend the old one", i, h->h_bc[i].kind, table[i].kind);
+    if ((size_t) n_table < h->h_bc.size()) return fail(LBM_B200_EINVAL, "a new handler table must extend the old one (%zu handlers)", h->h_bc.size());
     h->h_bc.assign(table, table + n_table);
-    h->h_kind.resize(n);
-    h->h_bcid.resize(n);
-    h->geom_dirty = true;
-    h->materialized = false;
-    const int rc = validate_maps(h, kind, bc_id);
-    CU(cudaStreamSynchronize(h->stream));     // the caller may release its arrays after this call
-    if (rc != 0) {
-        drop_staged_maps(h);
-        h->geom_unchecked = true;             // the next commit reports the same error again
-        return rc;
+    return sync_table(h);
+}
+
+int lbm_b200_paint_boxes(lbm_b200_t* h, const uint64_t* boxes6, const uint16_t* ids, int n)
+{
+    GUARD(h);
+    if (n < 0 || (n > 0 && (!boxes6 || !ids))) return fail(LBM_B200_EINVAL, "bad box list");
+    for (int b = 0; b < n; ++b) {
+        TRY(check_box(h, boxes6 + 6 * b, b));
+        if (ids[b] >= h->h_bc.size()) return fail(LBM_B200_EINVAL, "box %d: handler id %d outside the table (%zu handlers)", b, ids[b], h->h_bc.size());
     }
-    h->geom_unchecked = false;
+    if (n == 0) return 0;
+    TRY(before_geometry_change(h));
+    LayerSel sel;
+    TRY(select_layers(h, 0, &sel));
+    for (int b = 0; b < n; ++b) TRY(paint_box(h, sel, boxes6 + 6 * b, h->h_bc[ids[b]].kind, ids[b]));
+    mark_geometry_dirty(h);
     return 0;
 }
 
 int lbm_b200_set_boxes(lbm_b200_t* h, const uint64_t* boxes6, const lbm_b200_bc* table, int n)
 {
-    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    GUARD(h);
     if (n < 0 || (n > 0 && (!boxes6 || !table))) return fail(LBM_B200_EINVAL, "bad box list");
-    TRY(before_geometry_change(h));
-    drop_staged_maps(h);   // the host maps become the source of the next commit
-    const Layout& g = h->g;
+    TRY(check_table(table, n));
+    for (int b = 0; b < n; ++b) TRY(check_box(h, boxes6 + 6 * b, b));
+    if (h->h_bc.size() + (size_t) n > 65535) return fail(LBM_B200_EINVAL, "more than 65535 boundary handlers");
+    if (n == 0) return 0;
+    std::vector<uint16_t> ids(n);
     for (int b = 0; b < n; ++b) {
-        const uint64_t* e = boxes6 + 6 * b;
-        // the reference asserts these (domain.hpp:180-181)
-        if (!(e[1] >= e[0] && e[3] >= e[2] && e[5] >= e[4]))
-            return fail(LBM_B200_EINVAL, "box %d: end before begin", b);
-        if (!(e[1] < (uint64_t) g.xl + 2 && e[3] < (uint64_t) g.yl + 2 && e[5] < (uint64_t) h->zl_global + 2))
-            return fail(LBM_B200_EINVAL, "box %d: extent outside the domain", b);
-        const int k = table[b].kind;
-        if (!((k >= K_NOSLIP && k <= K_PRESSURE) || k == K_PARALLEL || k == K_PERIODIC || k == K_NULL || k == K_FLUID))
-            return fail(LBM_B200_EINVAL, "box %d: unknown kind %d", b, k);
-        if (h->h_bc.size() >= 65535) return fail(LBM_B200_EINVAL, "more than 65535 boundary handlers");
-        const uint16_t id = (uint16_t) h->h_bc.size();
+        ids[b] = (uint16_t) h->h_bc.size();
         h->h_bc.push_back(table[b]);
-        const long long zoff = h->z_first - 1;   // local z = global z - zoff
-        const long long lz0 = std::max<long long>((long long) e[4] - zoff, 0);
-        const long long lz1 = std::min<long long>((long long) e[5] - zoff, g.zl + 1);
-        for (long long z = lz0; z <= lz1; ++z)
-            for (uint64_t y = e[2]; y <= e[3]; ++y) {
-                const size_t row = ((size_t) z * (g.yl + 2) + y) * (g.xl + 2);
-                for (uint64_t x = e[0]; x <= e[1]; ++x) {
-                    h->h_kind[row + x] = (uint8_t) k;
-                    h->h_bcid[row + x] = id;
-                }
-            }
     }
-    h->geom_dirty = true;
-    h->materialized = false;
+    TRY(sync_table(h));
+    return lbm_b200_paint_boxes(h, boxes6, ids.data(), n);
+}
+
+int lbm_b200_set_geometry(lbm_b200_t* h, const uint8_t* kind, const uint16_t* bc_id, const lbm_b200_bc* table, int n_table)
+{
+    GUARD(h);
+    if (!kind) return fail(LBM_B200_EINVAL, "kind map is null");
+    TRY(check_table(table, n_table));
+    if (!bc_id && n_table > 1) return fail(LBM_B200_EINVAL, "bc_id map required for a table of %d handlers", n_table);
+    TRY(before_geometry_change(h));
+    // the maps are checked against the NEW table; on failure the old table comes back
+    std::vector<lbm_b200_bc> old_table = h->h_bc;
+    h->h_bc.assign(table, table + n_table);
+    TRY(sync_table(h));
+    unsplit(h);
+    LayerSel sel{ { &h->layer[0], nullptr }, 1 };
+    const int rc = upload_map_planes(h, kind, bc_id, 0, h->g.zl + 2, sel);
+    if (rc != 0) {
+        const std::string keep = g_error;
+        h->h_bc = old_table;
+        sync_table(h);
+        g_error = keep;
+        return rc;
+    }
+    h->null_tagged = false;
+    mark_geometry_dirty(h);
     return 0;
 }
 
-int lbm_b200_set_fluid_mask(lbm_b200_t* h, const uint8_t* mask)
+int lbm_b200_set_geometry_planes(lbm_b200_t* h, const uint8_t* kind, const uint16_t* bc_id, uint64_t z_begin, uint64_t z_count, int literal)
 {
-    if (!h) return fail(LBM_B200_EINVAL, "null handle");
-    if (!mask) return fail(LBM_B200_EINVAL, "mask is null");
-    if (h->h_bc.size() >= 65535) return fail(LBM_B200_EINVAL, "more than 65535 boundary handlers");
+    GUARD(h);
+    if (!kind || !bc_id) return fail(LBM_B200_EINVAL, "kind / bc_id map is null");
+    if (z_begin + z_count > (uint64_t) h->g.zl + 2) return fail(LBM_B200_EINVAL, "plane range outside the slab");
+    if (z_count == 0) return 0;
     TRY(before_geometry_change(h));
-    drop_staged_maps(h);
+    LayerSel sel;
+    TRY(select_layers(h, literal, &sel));
+    TRY(upload_map_planes(h, kind, bc_id, (int) z_begin, (int) z_count, sel));
+    mark_geometry_dirty(h);
+    return 0;
+}
+
+int lbm_b200_get_geometry_planes(lbm_b200_t* h, uint8_t* kind, uint16_t* bc_id, uint64_t z_begin, uint64_t z_count)
+{
+    GUARD(h);
+    if (z_begin + z_count > (uint64_t) h->g.zl + 2) return fail(LBM_B200_EINVAL, "plane range outside the slab");
+    if (z_count == 0 || (!kind && !bc_id)) return 0;
     const Layout& g = h->g;
-    lbm_b200_bc solid{};
-    solid.kind = LBM_B200_NOSLIP;
-    solid.rho = 1.0;
-    const uint16_t id = (uint16_t) h->h_bc.size();
-    h->h_bc.push_back(solid);
-    size_t i = 0;
-    for (int z = 1; z < g.zl + 1; ++z)
-        for (int y = 1; y < g.yl + 1; ++y) {
-            const size_t row = ((size_t) z * (g.yl + 2) + y) * (g.xl + 2);
-            for (int x = 1; x < g.xl + 1; ++x, ++i)
-                if (!mask[i]) {
-                    h->h_kind[row + x] = LBM_B200_NOSLIP;
-                    h->h_bcid[row + x] = id;
-                }
-        }
-    h->geom_dirty = true;
-    h->materialized = false;
+    const size_t n = (size_t) (g.xl + 2) * (g.yl + 2) * z_count;
+    DevBuf b8, b16;
+    if (kind) CU(cudaMalloc(&b8.p, n));
+    if (bc_id) CU(cudaMalloc(&b16.p, n * sizeof(uint16_t)));
+    const GeoLayer& L = h->layer[h->cur];
+    // unsplit layers: the tags of set_nonfluid_cells_nullcollide sit in one lattice only (see tag_null_cells)
+    const int former = !h->split && h->null_tagged && ((h->steps - h->null_tagged_at) & 1);
+    gather_maps_kernel<<<map_grid(g, (int) z_count), 128, 0, h->stream>>>(L.kind, L.bcid, h->d_bc, (int) h->h_bc.size(), b8.as<uint8_t>(),
+                                                                         b16.as<uint16_t>(), g, (int) z_begin, former);
+    h->launches++;
+    CU(cudaGetLastError());
+    if (kind) CU(cudaMemcpyAsync(kind, b8.p, n, cudaMemcpyDeviceToHost, h->stream));
+    if (bc_id) CU(cudaMemcpyAsync(bc_id, b16.p, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 int lbm_b200_get_kind(lbm_b200_t* h, uint8_t* kind)
 {
     if (!h || !kind) return fail(LBM_B200_EINVAL, "null argument");
-    memcpy(kind, h->h_kind.data(), h->ncell());
+    return lbm_b200_get_geometry_planes(h, kind, nullptr, 0, (uint64_t) h->g.zl + 2);
+}
+
+// mask: x-y planes of interior cells for the GLOBAL planes [mask_z_first, mask_z_first + mask_nz); cells whose
+// mask value is 0 take handler `id` of the table (id < 0: a NoSlipBoundary is appended for them)
+static int apply_fluid_mask(lbm_b200* h, const uint8_t* mask, int mask_z_first, int mask_nz, int literal, int id)
+{
+    if (!mask) return fail(LBM_B200_EINVAL, "mask is null");
+    if (id >= (int) h->h_bc.size()) return fail(LBM_B200_EINVAL, "handler id %d outside the table (%zu handlers)", id, h->h_bc.size());
+    if (id < 0 && h->h_bc.size() >= 65535) return fail(LBM_B200_EINVAL, "more than 65535 boundary handlers");
+    const Layout& g = h->g;
+    // local planes that are interior planes of the global domain and covered by the mask: own planes plus
+    // the replicas of the neighbours' edge planes
+    const int zoff = h->z_first - 1;                       // local z = global z - zoff
+    const int lo = std::max(std::max(mask_z_first - zoff, 1 - zoff), 0);
+    const int hi = std::min(std::min(mask_z_first + mask_nz - 1 - zoff, h->zl_global - zoff), g.zl + 1);
+    if (lo > hi) return 0;
+    TRY(before_geometry_change(h));
+    LayerSel sel;
+    TRY(select_layers(h, literal, &sel));
+    if (id < 0) {
+        lbm_b200_bc solid{};
+        solid.kind = LBM_B200_NOSLIP;      // read_vtk_point_file<M, NoSlipBoundary<M>> (io/scenario.h:161-162)
+        solid.rho = 1.0;
+        id = (int) h->h_bc.size();
+        h->h_bc.push_back(solid);
+        TRY(sync_table(h));
+    }
+    const size_t plane_cells = (size_t) g.xl * g.yl;
+    const int nz = hi - lo + 1;
+    const int first_mask_plane = lo + zoff - mask_z_first;     // index into `mask`
+    DevBuf buf;
+    CU(cudaMalloc(&buf.p, plane_cells * nz));
+    CU(cudaMemcpyAsync(buf.p, mask + plane_cells * first_mask_plane, plane_cells * nz, cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((g.xl + 127) / 128, g.yl, nz);
+    for (int l = 0; l < sel.n; ++l) {
+        paint_mask_kernel<<<grid, 128, 0, h->stream>>>(buf.as<uint8_t>(), sel.l[l]->kind, sel.l[l]->bcid, g, lo, lo,
+                                                       (uint8_t) h->h_bc[id].kind, (uint16_t) id);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    mark_geometry_dirty(h);
+    return 0;
+}
+
+int lbm_b200_set_fluid_mask(lbm_b200_t* h, const uint8_t* mask)
+{
+    GUARD(h);
+    return apply_fluid_mask(h, mask, h->z_first, h->g.zl, 0, -1);
+}
+int lbm_b200_set_fluid_mask_literal(lbm_b200_t* h, const uint8_t* mask)
+{
+    GUARD(h);
+    return apply_fluid_mask(h, mask, h->z_first, h->g.zl, 1, -1);
+}
+int lbm_b200_set_fluid_mask_global(lbm_b200_t* h, const uint8_t* mask, int literal)
+{
+    GUARD(h);
+    return apply_fluid_mask(h, mask, 1, h->zl_global, literal, -1);
+}
+int lbm_b200_paint_mask(lbm_b200_t* h, const uint8_t* mask, uint16_t id, int literal)
+{
+    GUARD(h);
+    return apply_fluid_mask(h, mask, 1, h->zl_global, literal, (int) id);
+}
+
+int lbm_b200_tag_null_cells(lbm_b200_t* h, int literal, uint64_t* n_tagged)
+{
+    GUARD(h);
+    if (n_tagged) *n_tagged = 0;
+    const Layout& g = h->g;
+    // which arrays take the tags: the collide field's own layer (literal, or already split -- the reference
+    // always goes through Domain::cell()), else the shared maps plus the step count for the read-back
+    if (literal || (!h->split && h->null_tagged && ((h->steps - h->null_tagged_at) & 1))) TRY(ensure_split(h));
+    GeoLayer& L = h->layer[h->cur];
+    CU(cudaMemsetAsync(h->d_counters + 4, 0, sizeof(unsigned int), h->stream));
+    dim3 grid((g.xl + 127) / 128, g.yl, g.zl);
+    dispatch_q(h->Q, [&](auto Qc) {
+        tag_null_kernel<decltype(Qc)::value><<<grid, 128, 0, h->stream>>>(L.kind, g, h->z_first, h->zl_global, h->d_counters + 4);
+        return 0;
+    });
+    h->launches++;
+    CU(cudaGetLastError());
+    unsigned int n = 0;
+    CU(cudaMemcpyAsync(&n, h->d_counters + 4, sizeof n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (n_tagged) *n_tagged = n;
+    if (n && !h->split) {
+        h->null_tagged = true;
+        h->null_tagged_at = h->steps;
+    }
+    // a tagged cell was not fluid before and has no fluid neighbour: link masks and populations do not
+    // change, only what the handler maps report
     return 0;
 }
 
@@ -901,18 +1365,50 @@ int lbm_b200_init_equilibrium(lbm_b200_t* h, const double* rho, const double* u)
 }
 
 // ---- checkpoint / restart (absent in the reference) ------------------------------
-// File: 64-byte header {magic "LBMB200\0", version, Q, xl, yl, zl_local, z_first, zl_global, steps, tau}
-// followed by the collide field as Q dense arrays in Domain::idx order (layout LBM_B200_SOA).
+// File: 64-byte header {magic "LBMB200\0", version, Q, xl, yl, zl_local, z_first, zl_global, arithmetic mode,
+// steps, tau, checksum of the collide field's handler-kind map} followed by the collide field and then the
+// stream field, each as Q dense arrays in Domain::idx order (layout LBM_B200_SOA).  The stream field carries
+// state too: ghost-shell cells that kept the fluid handler are collided in place in both lattices.
 namespace {
 struct CheckpointHeader {
     char magic[8];
     int32_t version, Q;
-    int32_t xl, yl, zl_local, z_first, zl_global, pad;
+    int32_t xl, yl, zl_local, z_first, zl_global, arithmetic;
     uint64_t steps;
     double tau;
-    uint64_t reserved;
+    uint64_t kind_hash;
 };
 static_assert(sizeof(CheckpointHeader) == 64, "checkpoint header layout");
+
+// FNV-1a over the dense kind map of one layer (tags of set_nonfluid_cells_nullcollide read as the former kind,
+// so that the checksum does not depend on the step parity)
+int hash_layer(lbm_b200* h, const GeoLayer& L, uint64_t* out)
+{
+    const Layout& g = h->g;
+    const size_t n = h->ncell();
+    DevBuf b8;
+    CU(cudaMalloc(&b8.p, n));
+    gather_maps_kernel<<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(L.kind, L.bcid, h->d_bc, (int) h->h_bc.size(), b8.as<uint8_t>(),
+                                                                    nullptr, g, 0, h->split ? 0 : 1);
+    h->launches++;
+    CU(cudaGetLastError());
+    std::vector<uint8_t> k(n);
+    CU(cudaMemcpyAsync(k.data(), b8.p, n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    uint64_t x = 1469598103934665603ull;
+    for (uint8_t b : k) { x ^= b; x *= 1099511628211ull; }
+    *out = x;
+    return 0;
+}
+// both lattices, independent of which one is the collide field at the moment
+int kind_hash(lbm_b200* h, uint64_t* out)
+{
+    uint64_t a = 0, b = 0;
+    TRY(hash_layer(h, h->layer[0], &a));
+    if (h->split) TRY(hash_layer(h, h->layer[1], &b));
+    *out = a + b;
+    return 0;
+}
 }
 
 int lbm_b200_save_checkpoint(lbm_b200_t* h, const char* path)
@@ -921,24 +1417,29 @@ int lbm_b200_save_checkpoint(lbm_b200_t* h, const char* path)
     if (!path) return fail(LBM_B200_EINVAL, "null path");
     TRY(materialize(h));
     const Layout& g = h->g;
-    FILE* fp = fopen(path, "wb");
-    if (!fp) return fail(LBM_B200_EINVAL, "cannot open %s for writing", path);
     CheckpointHeader hd{};
     memcpy(hd.magic, "LBMB200", 8);
-    hd.version = 1; hd.Q = h->Q;
+    hd.version = 2; hd.Q = h->Q;
     hd.xl = g.xl; hd.yl = g.yl; hd.zl_local = g.zl; hd.z_first = h->z_first; hd.zl_global = h->zl_global;
+    hd.arithmetic = h->exact ? LBM_B200_EXACT : LBM_B200_FAST;
     hd.steps = h->steps; hd.tau = h->tau;
+    TRY(kind_hash(h, &hd.kind_hash));
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(LBM_B200_EINVAL, "cannot open %s for writing", path);
     int rc = fwrite(&hd, sizeof hd, 1, fp) == 1 ? 0 : fail(LBM_B200_EINVAL, "write to %s failed", path);
     const size_t n = h->ncell();
     std::vector<double> buf(n);
     const size_t rows = (size_t) (g.yl + 2) * (g.zl + 2);
-    for (int q = 0; q < h->Q && rc == 0; ++q) {
-        const double* d = h->f[h->cur] + (size_t) q * g.qstride + X_SHIFT;
-        cudaError_t e = cudaMemcpy2DAsync(buf.data(), (g.xl + 2) * sizeof(double), d, g.P * sizeof(double),
-                                          (g.xl + 2) * sizeof(double), rows, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = fail(LBM_B200_ECUDA, "checkpoint download failed: %s", cudaGetErrorString(e));
-        else if (fwrite(buf.data(), sizeof(double), n, fp) != n) rc = fail(LBM_B200_EINVAL, "write to %s failed", path);
+    for (int field = 0; field < 2 && rc == 0; ++field) {
+        const double* base = h->f[field == 0 ? h->cur : 1 - h->cur];
+        for (int q = 0; q < h->Q && rc == 0; ++q) {
+            const double* d = base + (size_t) q * g.qstride + X_SHIFT;
+            cudaError_t e = cudaMemcpy2DAsync(buf.data(), (g.xl + 2) * sizeof(double), d, g.P * sizeof(double),
+                                              (g.xl + 2) * sizeof(double), rows, cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) rc = fail(LBM_B200_ECUDA, "checkpoint download failed: %s", cudaGetErrorString(e));
+            else if (fwrite(buf.data(), sizeof(double), n, fp) != n) rc = fail(LBM_B200_EINVAL, "write to %s failed", path);
+        }
     }
     if (fclose(fp) != 0 && rc == 0) rc = fail(LBM_B200_EINVAL, "closing %s failed", path);
     return rc;
@@ -953,24 +1454,39 @@ int lbm_b200_load_checkpoint(lbm_b200_t* h, const char* path)
     if (!fp) return fail(LBM_B200_EINVAL, "cannot open %s", path);
     CheckpointHeader hd{};
     int rc = 0;
-    if (fread(&hd, sizeof hd, 1, fp) != 1 || memcmp(hd.magic, "LBMB200", 8) != 0 || hd.version != 1)
-        rc = fail(LBM_B200_EINVAL, "%s is not a lbm_b200 checkpoint", path);
+    uint64_t my_hash = 0;
+    if (fread(&hd, sizeof hd, 1, fp) != 1 || memcmp(hd.magic, "LBMB200", 8) != 0 || hd.version != 2)
+        rc = fail(LBM_B200_EINVAL, "%s is not a lbm_b200 checkpoint (version 2)", path);
     else if (hd.Q != h->Q || hd.xl != g.xl || hd.yl != g.yl || hd.zl_local != g.zl || hd.z_first != h->z_first || hd.zl_global != h->zl_global)
         rc = fail(LBM_B200_EINVAL, "%s holds D3Q%d %dx%dx%d (slab at %d of %d), this domain is D3Q%d %dx%dx%d (slab at %d of %d)", path,
                   hd.Q, hd.xl, hd.yl, hd.zl_local, hd.z_first, hd.zl_global, h->Q, g.xl, g.yl, g.zl, h->z_first, h->zl_global);
+    else if (hd.arithmetic != (h->exact ? LBM_B200_EXACT : LBM_B200_FAST))
+        rc = fail(LBM_B200_EINVAL, "%s was written in %s arithmetic, this domain runs in %s arithmetic", path,
+                  hd.arithmetic == LBM_B200_EXACT ? "exact" : "fast", h->exact ? "exact" : "fast");
+    else if ((rc = kind_hash(h, &my_hash)) == 0 && my_hash != hd.kind_hash)
+        rc = fail(LBM_B200_EINVAL, "%s was written under a different geometry (handler-map checksum differs): re-apply the scenario first", path);
     const size_t n = h->ncell();
     std::vector<double> buf(rc == 0 ? n : 0);
     const size_t rows = (size_t) (g.yl + 2) * (g.zl + 2);
-    for (int q = 0; q < h->Q && rc == 0; ++q) {
-        if (fread(buf.data(), sizeof(double), n, fp) != n) { rc = fail(LBM_B200_EINVAL, "%s is truncated", path); break; }
-        double* d = h->f[h->cur] + (size_t) q * g.qstride + X_SHIFT;
-        cudaError_t e = cudaMemcpy2DAsync(d, g.P * sizeof(double), buf.data(), (g.xl + 2) * sizeof(double),
-                                          (g.xl + 2) * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = fail(LBM_B200_ECUDA, "checkpoint upload failed: %s", cudaGetErrorString(e));
+    for (int field = 0; field < 2 && rc == 0; ++field) {
+        double* base = h->f[field == 0 ? h->cur : 1 - h->cur];
+        for (int q = 0; q < h->Q && rc == 0; ++q) {
+            if (fread(buf.data(), sizeof(double), n, fp) != n) { rc = fail(LBM_B200_EINVAL, "%s is truncated", path); break; }
+            double* d = base + (size_t) q * g.qstride + X_SHIFT;
+            cudaError_t e = cudaMemcpy2DAsync(d, g.P * sizeof(double), buf.data(), (g.xl + 2) * sizeof(double),
+                                              (g.xl + 2) * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) rc = fail(LBM_B200_ECUDA, "checkpoint upload failed: %s", cudaGetErrorString(e));
+        }
     }
     fclose(fp);
     if (rc == 0) {
+        // handlers belong to lattices: if the file's collide field is the other lattice (odd distance in steps),
+        // the layers trade places; null tags follow the absolute step count by themselves
+        if (h->split && ((hd.steps - h->steps) & 1)) {
+            std::swap(h->layer[0], h->layer[1]);
+            mark_geometry_dirty(h);
+        }
         h->steps = hd.steps;
         h->first = true;          // boundary cells hold the stored (materialised) values again
         h->materialized = true;
@@ -982,32 +1498,45 @@ int lbm_b200_load_checkpoint(lbm_b200_t* h, const char* path)
 int lbm_b200_step(lbm_b200_t* h, uint64_t n_steps)
 {
     GUARD(h);
-    if (h->edges_done) return fail(LBM_B200_ESTATE, "a split-phase step is in flight");
-    TRY(commit_geometry(h));
-    if ((h->ring_lo && !h->peer_f[LBM_B200_DOWN][0]) || (h->ring_hi && !h->peer_f[LBM_B200_UP][0]))
-        return fail(LBM_B200_ESTATE, "periodic z on a multi-slab domain needs the first and last slab connected as a ring "
-                    "(lbm_b200_connect / lbm_b200_connect_local on that side)");
+    TRY(ready_to_step(h));
     CU(cudaEventRecord(h->ev_a, h->stream));
-    for (uint64_t s = 0; s < n_steps; ++s) {
-        if (has_peers(h) && h->g.zl >= 3) {
-            // Only the two edge planes read ghost planes and feed the neighbours, so only they take
-            // part in the hand-shake; the interior sweep that follows gives every neighbour a whole
-            // step of slack before its next wait.
-            TRY(halo_wait(h));
-            TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1));
-            TRY(halo_signal(h));
-            TRY(launch_sweep(h, 2, h->g.zl - 2, false));
-        } else {
-            TRY(halo_wait(h));
-            TRY(launch_sweep(h, 1, h->g.zl, true));
-            TRY(halo_signal(h));
-        }
-        TRY(launch_ghost(h));
-        finish_step(h);
-    }
+    TRY(enqueue_steps(h, n_steps));
     CU(cudaEventRecord(h->ev_b, h->stream));
     h->timed = true;
     return 0;
+}
+
+int lbm_b200_step_group(lbm_b200_t* const* hs, int n, uint64_t n_steps)
+{
+    if (n < 0 || (n > 0 && !hs)) return fail(LBM_B200_EINVAL, "bad handle list");
+    for (int i = 0; i < n; ++i)
+        if (!hs[i]) return fail(LBM_B200_EINVAL, "null handle");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    int rc = 0;
+    for (int i = 0; i < n && rc == 0; ++i) {
+        if (cudaSetDevice(hs[i]->device) != cudaSuccess) rc = fail(LBM_B200_ECUDA, "cannot select CUDA device %d", hs[i]->device);
+        if (rc == 0) rc = ready_to_step(hs[i]);
+        if (rc == 0 && cudaEventRecord(hs[i]->ev_a, hs[i]->stream) != cudaSuccess) rc = fail(LBM_B200_ECUDA, "cudaEventRecord failed");
+    }
+    // Runs of at most GRAPH_STEPS steps per slab, slab after slab: a slab's wait kernel never sits in front
+    // of a device queue for longer than it takes the host to submit the same run to its neighbours.
+    uint64_t done = 0;
+    while (rc == 0 && done < n_steps) {
+        const uint64_t run = std::min<uint64_t>(lbm_b200::GRAPH_STEPS, n_steps - done);
+        for (int i = 0; i < n && rc == 0; ++i) {
+            if (cudaSetDevice(hs[i]->device) != cudaSuccess) rc = fail(LBM_B200_ECUDA, "cannot select CUDA device %d", hs[i]->device);
+            if (rc == 0) rc = enqueue_steps(hs[i], run);
+        }
+        done += run;
+    }
+    for (int i = 0; i < n && rc == 0; ++i) {
+        if (cudaSetDevice(hs[i]->device) != cudaSuccess || cudaEventRecord(hs[i]->ev_b, hs[i]->stream) != cudaSuccess)
+            rc = fail(LBM_B200_ECUDA, "cudaEventRecord failed");
+        hs[i]->timed = true;
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
 }
 
 int lbm_b200_sync(lbm_b200_t* h)
@@ -1038,9 +1567,19 @@ int lbm_b200_launch_count(lbm_b200_t* h, uint64_t* n)
 uint64_t lbm_b200_steps_done(lbm_b200_t* h) { return h ? h->steps : 0; }
 
 // ---- read-out -----------------------------------------------------------------
-int lbm_b200_macroscopic(lbm_b200_t* h, double* rho, double* u)
+int lbm_b200_macroscopic_end(lbm_b200_t* h)
 {
     GUARD(h);
+    if (!h->readout_pending) return 0;
+    h->readout_pending = false;
+    CU(cudaEventSynchronize(h->ev_copied));
+    return 0;
+}
+
+int lbm_b200_macroscopic_begin(lbm_b200_t* h, double* rho, double* u)
+{
+    GUARD(h);
+    TRY(lbm_b200_macroscopic_end(h));     // the staging arrays are about to be overwritten
     TRY(materialize(h));
     const Layout& g = h->g;
     const size_t n = (size_t) g.xl * g.yl * g.zl;
@@ -1048,17 +1587,125 @@ int lbm_b200_macroscopic(lbm_b200_t* h, double* rho, double* u)
     if (u && !h->d_u) CU(cudaMalloc(&h->d_u, 3 * n * sizeof(double)));
     double* d_rho = rho ? h->d_rho : nullptr;
     double* d_u = u ? h->d_u : nullptr;
-    dim3 grid((g.xl + 127) / 128, g.yl, g.zl);
-    dispatch_q(h->Q, [&](auto Qc) {
-        macroscopic_kernel<decltype(Qc)::value><<<grid, 128, 0, h->stream>>>(h->f[h->cur], g, d_rho, d_u);
-        return 0;
-    });
-    h->launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && rho) e = cudaMemcpyAsync(rho, d_rho, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess && u) e = cudaMemcpyAsync(u, d_u, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) return fail(LBM_B200_ECUDA, "macroscopic read-out failed: %s", cudaGetErrorString(e));
+    // z chunks: the reduction of chunk k+1 (compute stream) runs while chunk k crosses PCIe (copy stream);
+    // the whole snapshot is reduced before any later step touches the lattice, the copies then overlap
+    // with those steps
+    const int chunks = std::min(lbm_b200::READOUT_CHUNKS, g.zl);
+    const size_t plane = (size_t) g.xl * g.yl;
+    for (int c = 0; c < chunks; ++c) {
+        const int z0 = (int) ((long long) g.zl * c / chunks), z1 = (int) ((long long) g.zl * (c + 1) / chunks);
+        if (z1 <= z0) continue;
+        dim3 grid((g.xl + 127) / 128, g.yl, z1 - z0);
+        dispatch_q(h->Q, [&](auto Qc) {
+            macroscopic_kernel<decltype(Qc)::value><<<grid, 128, 0, h->stream>>>(h->f[h->cur], g, d_rho, d_u, z0);
+            return 0;
+        });
+        h->launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(h->ev_chunk[c], h->stream));
+        CU(cudaStreamWaitEvent(h->copy_stream, h->ev_chunk[c], 0));
+        const size_t off = plane * z0, cnt = plane * (z1 - z0);
+        if (rho) CU(cudaMemcpyAsync(rho + off, d_rho + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (u) CU(cudaMemcpyAsync(u + 3 * off, d_u + 3 * off, 3 * cnt * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    CU(cudaEventRecord(h->ev_copied, h->copy_stream));
+    h->readout_pending = true;
+    return 0;
+}
+
+int lbm_b200_macroscopic(lbm_b200_t* h, double* rho, double* u)
+{
+    TRY(lbm_b200_macroscopic_begin(h, rho, u));
+    return lbm_b200_macroscopic_end(h);
+}
+
+// ---- host memory next to a GPU ---------------------------------------------------------------------
+namespace {
+std::mutex g_host_mutex;
+std::map<void*, size_t> g_host_blocks;     // pointer -> bytes (posix_memalign + cudaHostRegister)
+
+// CPUs of the NUMA node the device hangs off; false where the topology is unknown (containers, 1 node)
+bool device_cpus(int device, cpu_set_t* set)
+{
+    char bus[32] = {};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (char* c = bus; *c; ++c) *c = (char) tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* fp = fopen(path, "r");
+    if (!fp) return false;
+    int node = -1;
+    const int got = fscanf(fp, "%d", &node);
+    fclose(fp);
+    if (got != 1 || node < 0) return false;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    fp = fopen(path, "r");
+    if (!fp) return false;
+    char list[4096] = {};
+    const bool ok = fgets(list, sizeof list, fp) != nullptr;
+    fclose(fp);
+    if (!ok) return false;
+    CPU_ZERO(set);
+    int count = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1) b = a;
+        if (k < 1) continue;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, set); ++count; }
+    }
+    return count > 0;
+}
+}
+
+int lbm_b200_bind_host_thread(int device)
+{
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return fail(LBM_B200_ECUDA, "cudaGetDevice failed");
+    cpu_set_t set;
+    if (device_cpus(device, &set)) sched_setaffinity(0, sizeof set, &set);
+    return 0;
+}
+
+int lbm_b200_host_alloc(void** ptr, size_t bytes, int device)
+{
+    if (!ptr || bytes == 0) return fail(LBM_B200_EINVAL, "bad host allocation request");
+    *ptr = nullptr;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return fail(LBM_B200_ECUDA, "cudaGetDevice failed");
+    // first touch from a thread pinned to the GPU's node places the pages there; then page-lock them
+    cpu_set_t old_set, near_set;
+    const bool have_old = sched_getaffinity(0, sizeof old_set, &old_set) == 0;
+    const bool moved = have_old && device_cpus(device, &near_set) && sched_setaffinity(0, sizeof near_set, &near_set) == 0;
+    void* p = nullptr;
+    const size_t rounded = (bytes + 4095) / 4096 * 4096;
+    int rc = 0;
+    if (posix_memalign(&p, 4096, rounded) != 0) rc = fail(LBM_B200_ENOMEM, "host allocation of %zu bytes failed", bytes);
+    if (rc == 0) {
+        for (size_t o = 0; o < rounded; o += 4096) ((volatile char*) p)[o] = 0;
+        const cudaError_t e = cudaHostRegister(p, rounded, cudaHostRegisterPortable);
+        if (e != cudaSuccess) {
+            free(p);
+            cudaGetLastError();
+            rc = fail(LBM_B200_ECUDA, "cudaHostRegister of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+    if (rc != 0) return rc;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    g_host_blocks[p] = rounded;
+    *ptr = p;
+    return 0;
+}
+
+int lbm_b200_host_free(void* ptr)
+{
+    if (!ptr) return 0;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    auto it = g_host_blocks.find(ptr);
+    if (it == g_host_blocks.end()) return fail(LBM_B200_EINVAL, "pointer was not returned by lbm_b200_host_alloc");
+    cudaHostUnregister(ptr);
+    cudaGetLastError();
+    free(ptr);
+    g_host_blocks.erase(it);
     return 0;
 }
 
@@ -1073,7 +1720,7 @@ int lbm_b200_diagnostics(lbm_b200_t* h, double* mass, double* kinetic, double* u
     CU(cudaMalloc(&part_buf.p, nblk * 3 * sizeof(double)));
     double* d_part = part_buf.as<double>();
     dispatch_q(h->Q, [&](auto Qc) {
-        diagnostics_kernel<decltype(Qc)::value><<<grid, 128, 0, h->stream>>>(h->f[h->cur], h->d_kind, g, d_part);
+        diagnostics_kernel<decltype(Qc)::value><<<grid, 128, 0, h->stream>>>(h->f[h->cur], h->layer[h->cur].kind, g, d_part);
         return 0;
     });
     h->launches++;
@@ -1120,7 +1767,8 @@ int lbm_b200_halo_plane(lbm_b200_t* h, int buffer, int side, int k, int recv, vo
     int z;
     if (side == LBM_B200_UP) z = recv ? g.zl + 1 : g.zl;
     else z = recv ? 0 : 1;
-    *ptr = h->f[buffer] + (size_t) q_found * g.qstride + (size_t) z * g.plane;
+    // the cells of plane z occupy [z*plane + X_SHIFT, (z+1)*plane + X_SHIFT): rows are shifted by X_SHIFT elements
+    *ptr = h->f[buffer] + (size_t) q_found * g.qstride + (size_t) z * g.plane + X_SHIFT;
     return 0;
 }
 
@@ -1130,9 +1778,9 @@ int lbm_b200_step_edges(lbm_b200_t* h)
 {
     GUARD(h);
     if (h->edges_done) return fail(LBM_B200_ESTATE, "step_edges called twice");
-    TRY(commit_geometry(h));
-    if (h->g.zl > 1) TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1));
-    else TRY(launch_sweep(h, 1, 1, true));
+    TRY(ready_to_step(h));
+    if (h->g.zl > 1) TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1, SWEEP_INLINE));
+    else TRY(launch_sweep(h, 1, 1, true, 1, SWEEP_INLINE));
     h->edges_done = true;
     return 0;
 }
@@ -1140,8 +1788,8 @@ int lbm_b200_step_interior(lbm_b200_t* h)
 {
     GUARD(h);
     if (!h->edges_done) return fail(LBM_B200_ESTATE, "step_interior before step_edges");
-    TRY(launch_sweep(h, 2, h->g.zl - 2, true));
-    TRY(launch_ghost(h));
+    TRY(sweep_planes(h, 2, h->g.zl - 2, true));
+    TRY(launch_inplace(h));
     return 0;
 }
 int lbm_b200_step_finish(lbm_b200_t* h)
@@ -1209,6 +1857,7 @@ static int connect_common(lbm_b200* h, int side, double* base, unsigned long lon
     // my top plane feeds the upper neighbour's ghost plane 0; my bottom plane the
     // lower neighbour's ghost plane zl_nb+1
     h->peer_off[side] = side == LBM_B200_UP ? 0 : (zl + 1) * plane;
+    drop_graphs(h);
     return 0;
 }
 
@@ -1241,6 +1890,7 @@ int lbm_b200_disconnect(lbm_b200_t* h)
 {
     GUARD(h);
     CU(cudaStreamSynchronize(h->stream));
+    drop_graphs(h);
     if (h->peer_ipc_shared) h->peer_ipc_base[1] = nullptr;   // mapped once
     h->peer_ipc_shared = false;
     for (int s = 0; s < 2; ++s) {

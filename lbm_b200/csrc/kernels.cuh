@@ -26,7 +26,9 @@ enum : int {
     K_INFLOW = 5, K_PRESSURE = 6, K_NULL = 7, K_PARALLEL = 8, K_PERIODIC = 9, K_COUNT = 10
 };
 
-constexpr uint32_t MASK_SKIP = 0x80000000u;   // not an interior fluid cell
+constexpr uint32_t MASK_SKIP = 0x80000000u;       // not streamed: not an interior cell, or not fluid in the source lattice
+constexpr uint32_t MASK_NOCOLLIDE = 0x40000000u;  // streamed, but the destination lattice's handler is not the fluid one
+                                                  // (only when the two lattices carry different handlers, see GeoLayer)
 constexpr int X_SHIFT = 15;                   // element offset of x = 0 inside a row
 
 struct BcRec {          // one boundary handler object, device copy
@@ -340,34 +342,12 @@ template <int Q> struct MinBlocks { static constexpr int value = Q == 15 ? LBM_M
 #define LBM_ST(ptr, v) (*(ptr) = (v))
 #endif
 
-// Everything after the pull: replace the directions whose source is not fluid (link-wise boundary
-// values), collide, store, and hand slab-edge populations to the neighbour.  `f` holds the values
-// pulled speculatively for ALL directions; `m` is the cell's link mask (0 for bulk cells).
+// Collide, store, and hand slab-edge populations to the neighbour.  `f` holds the streamed populations.
 template <int Q, bool EXACT>
-__device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q], const uint32_t m,
-                                            const int i, const int x, const int y, const int z)
+__device__ __forceinline__ void collide_and_store(const SweepParams& p, double (&f)[Q], const int i, const int z)
 {
     using L = Lattice<Q>;
     const Layout& g = p.g;
-    if (m != 0) {
-        OwnMoments om;
-        om.have = false;
-        static_for<Q>([&](auto I) {
-            constexpr int q = decltype(I)::value;
-            if (m & (1u << q)) {
-                const int s = i - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
-                const int k = p.kind[s];
-                if (k == K_PERIODIC) {
-                    const int sx = wrap1(x - L::cx(q), g.xl), sy = wrap1(y - L::cy(q), g.yl);
-                    const int sz = p.wrap_z ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
-                    f[q] = p.src[q * g.qstride + cell_at(g, sx, sy, sz)];
-                } else if (!p.first) {   // first step: the stored value already pulled is the answer
-                    f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, p.bc + p.bcid[s], om);
-                }
-            }
-        });
-    }
-
     bgk_collide<Q, EXACT>(f, p.tau, p.omega);
 
     static_for<Q>([&](auto I) {
@@ -391,7 +371,50 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
     }
 }
 
+// Everything after the pull for a cell next to a wall: replace the directions whose source is not fluid
+// (link-wise boundary values), then collide and store.  `f` holds the values pulled speculatively for ALL
+// directions; `m` is the cell's link mask (non-zero).
 template <int Q, bool EXACT>
+__device__ __forceinline__ void finish_wall_cell(const SweepParams& p, double (&f)[Q], const uint32_t m,
+                                                 const int i, const int x, const int y, const int z)
+{
+    using L = Lattice<Q>;
+    const Layout& g = p.g;
+    OwnMoments om;
+    om.have = false;
+    static_for<Q>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        if (m & (1u << q)) {
+            const int s = i - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
+            const int k = p.kind[s];
+            if (k == K_PERIODIC) {
+                const int sx = wrap1(x - L::cx(q), g.xl), sy = wrap1(y - L::cy(q), g.yl);
+                const int sz = p.wrap_z ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
+                f[q] = p.src[q * g.qstride + cell_at(g, sx, sy, sz)];
+            } else if (!p.first) {   // first step: the stored value already pulled is the answer
+                f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, p.bc + p.bcid[s], om);
+            }
+        }
+    });
+    if (m & MASK_NOCOLLIDE) {   // streamed into a cell whose handler in the destination lattice is a boundary
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            p.dstq[q][i] = f[q];
+        });
+        return;
+    }
+    collide_and_store<Q, EXACT>(p, f, i, z);
+}
+
+// How a sweep launch treats cells whose bit is set in `bits` (next to a wall, or not streamed at all):
+//   SWEEP_INLINE   handles them itself (link path inside the kernel); used for the two edge planes of a slab
+//   SWEEP_BULK     leaves them to wall_kernel; Q pulls and the bit are requested together (one DRAM round trip)
+//   SWEEP_CHECKED  leaves them to wall_kernel and looks at the bit BEFORE pulling: a flagged cell costs one
+//                  read of the (L2-resident) bit map instead of Q wasted pulls -- for geometries with large
+//                  solid regions (pipe.vtk: 44 % of the cells are solid)
+enum : int { SWEEP_INLINE = 0, SWEEP_BULK = 1, SWEEP_CHECKED = 2 };
+
+template <int Q, bool EXACT, int MODE>
 __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_kernel(const SweepParams p)
 {
     const Layout& g = p.g;
@@ -403,17 +426,94 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
     const int i = cell_at(g, x, y, z);
     // The link bit and the Q pulled populations are requested TOGETHER: every pull source of an
     // interior cell exists in memory (ghost shell), so the loads need not wait for the mask.  One
-    // DRAM round trip per cell instead of two dependent ones; for the ~1 % of cells next to a wall
-    // the flagged directions are replaced afterwards.  Bulk cells read 1/8 byte of map, not 4.
+    // DRAM round trip per cell instead of two dependent ones.  Bulk cells read 1/8 byte of map, not 4.
     const uint32_t word = p.bits[i >> 5];
+    if constexpr (MODE == SWEEP_CHECKED) {
+        if ((word >> (i & 31)) & 1u) return;
+    }
     double f[Q];
     static_for<Q>([&](auto I) {
         constexpr int q = decltype(I)::value;
         f[q] = LBM_LD(p.srcq[q] + i);
     });
-    const uint32_t m = ((word >> (i & 31)) & 1u) ? p.mask[i] : 0u;
-    if (m & MASK_SKIP) return;
-    finish_cell<Q, EXACT>(p, f, m, i, x, y, z);
+    if constexpr (MODE == SWEEP_INLINE) {
+        const uint32_t m = ((word >> (i & 31)) & 1u) ? p.mask[i] : 0u;
+        if (m & MASK_SKIP) return;
+        if (m != 0) {
+            finish_wall_cell<Q, EXACT>(p, f, m, i, x, y, z);
+            return;
+        }
+    } else if constexpr (MODE == SWEEP_BULK) {
+        if ((word >> (i & 31)) & 1u) return;
+    }
+    collide_and_store<Q, EXACT>(p, f, i, z);
+}
+
+// K1w: the streamed cells next to a wall, one thread each, from the index list built at geometry commit
+// (sorted by cell index, so whole wall planes are still read and written in coalesced runs).  Every lane
+// takes the link path, which a sweep warp with a single wall cell would execute for one lane only.
+template <int Q, bool EXACT>
+__global__ void __launch_bounds__(128) wall_kernel(const SweepParams p, const int* __restrict__ cells, const int n)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const Layout& g = p.g;
+    const int i = cells[t];
+    const int c = i - X_SHIFT;
+    const int z = c / g.plane;
+    const int r = c - z * g.plane;
+    const int y = r / g.P;
+    const int x = r - y * g.P;
+    const uint32_t m = p.mask[i];
+    double f[Q];
+    static_for<Q>([&](auto I) {
+        constexpr int q = decltype(I)::value;
+        f[q] = p.srcq[q][i];
+    });
+    finish_wall_cell<Q, EXACT>(p, f, m, i, x, y, z);
+}
+
+// wall-cell list, pass 1: streamed cells with a non-zero link mask per x-row (one warp per row)
+__global__ void wall_count_kernel(const uint32_t* __restrict__ mask, const Layout g, int* __restrict__ row_count)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // over interior rows: (z-1)*yl + (y-1)
+    const int lane = threadIdx.x & 31;
+    if (row >= g.yl * g.zl) return;
+    const int z = 1 + row / g.yl, y = 1 + row % g.yl;
+    int n = 0;
+    for (int x0 = 1; x0 <= g.xl; x0 += 32) {
+        const int x = x0 + lane;
+        bool wall = false;
+        if (x <= g.xl) {
+            const uint32_t m = mask[cell_at(g, x, y, z)];
+            wall = m != 0 && !(m & MASK_SKIP);
+        }
+        n += __popc(__ballot_sync(0xffffffffu, wall));
+    }
+    if (lane == 0) row_count[row] = n;
+}
+// pass 2: row_start = exclusive prefix sum of row_count
+__global__ void wall_fill_kernel(const uint32_t* __restrict__ mask, const Layout g, const int* __restrict__ row_start,
+                                 int* __restrict__ cells)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= g.yl * g.zl) return;
+    const int z = 1 + row / g.yl, y = 1 + row % g.yl;
+    int base = row_start[row];
+    for (int x0 = 1; x0 <= g.xl; x0 += 32) {
+        const int x = x0 + lane;
+        bool wall = false;
+        int i = 0;
+        if (x <= g.xl) {
+            i = cell_at(g, x, y, z);
+            const uint32_t m = mask[i];
+            wall = m != 0 && !(m & MASK_SKIP);
+        }
+        const unsigned int b = __ballot_sync(0xffffffffu, wall);
+        if (wall) cells[base + __popc(b & ((1u << lane) - 1u))] = i;
+        base += __popc(b);
+    }
 }
 
 // K1g: ghost-shell cells that kept the fluid handler are BGK-collided in place in
@@ -438,16 +538,20 @@ __global__ void ghost_fluid_kernel(double* __restrict__ field, long long qstride
 template <int Q, bool EXACT>
 __global__ void materialize_kernel(double* __restrict__ field, const uint8_t* __restrict__ kind,
                                    const uint16_t* __restrict__ bcid, const BcRec* __restrict__ bc, const Layout g,
-                                   const int z_lo_open, const int z_hi_open)
+                                   const int lo_interface, const int hi_interface, const int z_lo_open, const int z_hi_open)
 {
-    // z_lo_open / z_hi_open: the ghost plane on that side is a slab interface whose cells are interior
-    // cells of the neighbour slab (their full populations were pushed here before this kernel)
+    // lo/hi_interface: the ghost plane on that side is a slab interface, its cells are interior cells of the
+    // neighbour slab.  z_lo_open / z_hi_open: the neighbour's FULL edge plane was pushed there for this time
+    // level (lbm_b200_halo_push_all), so links from our boundary cells into it can be evaluated too.
+    // Boundary cells INSIDE an interface ghost plane are the neighbour's, but their entries that point into
+    // our own interior are read by our edge-plane cells when the next sweep pulls stored values (`first`);
+    // those depend on our own cells only and are always written here.
     using L = Lattice<Q>;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int z = blockIdx.z;
     if (x > g.xl + 1) return;
-    if ((z == 0 && z_lo_open) || (z == g.zl + 1 && z_hi_open)) return;   // the neighbour's cells
+    const bool in_interface = (z == 0 && lo_interface) || (z == g.zl + 1 && hi_interface);
     const int b = cell_at(g, x, y, z);
     const int k = kind[b];
     if (k < K_NOSLIP || k > K_PRESSURE) return;
@@ -455,8 +559,9 @@ __global__ void materialize_kernel(double* __restrict__ field, const uint8_t* __
     static_for<Q>([&](auto I) {
         constexpr int q = decltype(I)::value;
         const int nx = x + L::cx(q), ny = y + L::cy(q), nz = z + L::cz(q);
-        const bool inb = nx > 0 && nx < g.xl + 1 && ny > 0 && ny < g.yl + 1
-                && (nz > 0 || z_lo_open) && (nz < g.zl + 1 || z_hi_open) && nz >= 0 && nz <= g.zl + 1;
+        bool inb = nx > 0 && nx < g.xl + 1 && ny > 0 && ny < g.yl + 1;
+        if (in_interface) inb = inb && nz > 0 && nz < g.zl + 1;
+        else inb = inb && (nz > 0 || (nz == 0 && z_lo_open)) && (nz < g.zl + 1 || (nz == g.zl + 1 && z_hi_open));
         if (inb) {
             const int n = b + (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
             if (kind[n] == K_FLUID) {
@@ -472,11 +577,11 @@ __global__ void materialize_kernel(double* __restrict__ field, const uint8_t* __
 // always in the reference's association.  Dense outputs in z,y,x order.
 template <int Q>
 __global__ void macroscopic_kernel(const double* __restrict__ field, const Layout g,
-                                   double* __restrict__ rho_out, double* __restrict__ u_out)
+                                   double* __restrict__ rho_out, double* __restrict__ u_out, const int z_begin)
 {
     const int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     const int y = 1 + blockIdx.y;
-    const int z = 1 + blockIdx.z;
+    const int z = 1 + z_begin + blockIdx.z;
     if (x > g.xl) return;
     const int i = cell_at(g, x, y, z);
     double f[Q];
@@ -546,10 +651,21 @@ __global__ void fill_weights_kernel(double* __restrict__ field, long long qstrid
         field[i] = T.w[i / qstride];
 }
 
-// link mask: bit q set <=> the pull source X - c_q of interior fluid cell X is not fluid
+// Link mask of the step  src lattice -> dst lattice.  Handlers belong to lattices (cell.h:15), and the
+// reference decides "is streamed" with the source lattice's handlers (domain.hpp:124, before the swap) and
+// "is collided" with the destination's (domain.hpp:148-165, after it).  Normally both lattices carry the
+// same handlers (kind_src == kind_dst).
+//   bit q           the pull source X - c_q of streamed cell X is not fluid (in the source lattice)
+//   MASK_SKIP       X is not streamed
+//   MASK_NOCOLLIDE  X is streamed but not BGK-collided
+// counters[0] += cells that are collided in place without being streamed (fluid in the destination lattice,
+// but in the ghost shell or not fluid in the source lattice; domain.hpp:147-155 loops 0..l+1);
+// counters[1] |= 1 if a z ghost plane of the physical shell carries PERIODIC;
+// counters[3] += interior cells with a non-zero mask.
 template <int Q>
-__global__ void build_mask_kernel(const uint8_t* __restrict__ kind, uint32_t* __restrict__ mask,
-                                  uint32_t* __restrict__ bits, const Layout g)
+__global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const uint8_t* __restrict__ kind_dst,
+                                  uint32_t* __restrict__ mask, uint32_t* __restrict__ bits, const Layout g,
+                                  const int lo_interface, const int hi_interface, unsigned int* __restrict__ counters)
 {
     const Tables<Q>& T = tables<Q>();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -558,17 +674,150 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ kind, uint32_t* __
     if (x > g.xl + 1) return;
     const int i = cell_at(g, x, y, z);
     const bool interior = x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1;
+    const bool streamed = interior && kind_src[i] == K_FLUID;
     uint32_t m = 0;
-    if (!interior || kind[i] != K_FLUID) {
+    if (!streamed) {
         m = MASK_SKIP;
     } else {
         for (int q = 0; q < Q; ++q) {
             const int s = i - (T.c[q][2] * g.plane + T.c[q][1] * g.P + T.c[q][0]);
-            if (kind[s] != K_FLUID) m |= 1u << q;
+            if (kind_src[s] != K_FLUID) m |= 1u << q;
         }
+        if (kind_dst[i] != K_FLUID) m |= MASK_NOCOLLIDE;
     }
     mask[i] = m;
     if (m) atomicOr(&bits[i >> 5], 1u << (i & 31));   // bits zeroed by the caller
+    if (m && interior) atomicAdd(&counters[3], 1u);
+    const bool neighbours_cell = (z == 0 && lo_interface) || (z == g.zl + 1 && hi_interface);
+    if (!neighbours_cell) {
+        if (!streamed && kind_dst[i] == K_FLUID) atomicAdd(&counters[0], 1u);
+        if ((z == 0 || z == g.zl + 1) && kind_src[i] == K_PERIODIC) atomicOr(&counters[1], 1u);
+    }
+}
+
+// second pass, only when the first one counted something: the list of in-place collided cells
+__global__ void collect_inplace_kernel(const uint8_t* __restrict__ kind_src, const uint8_t* __restrict__ kind_dst,
+                                       const Layout g, const int lo_interface, const int hi_interface,
+                                       int* __restrict__ list, unsigned int capacity, unsigned int* __restrict__ cursor)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int z = blockIdx.z;
+    if (x > g.xl + 1) return;
+    if ((z == 0 && lo_interface) || (z == g.zl + 1 && hi_interface)) return;
+    const int i = cell_at(g, x, y, z);
+    const bool interior = x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1;
+    const bool streamed = interior && kind_src[i] == K_FLUID;
+    if (!streamed && kind_dst[i] == K_FLUID) {
+        const unsigned int slot = atomicAdd(cursor, 1u);
+        if (slot < capacity) list[slot] = i;
+    }
+}
+
+// Domain::setBoundaryCondition (domain.hpp:185-193) for one inclusive box in LOCAL coordinates
+__global__ void paint_box_kernel(uint8_t* __restrict__ kind, uint16_t* __restrict__ bcid, const Layout g,
+                                 int x0, int y0, int z0, int nx, int ny, uint8_t k, uint16_t id)
+{
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dx >= nx) return;
+    const int i = cell_at(g, x0 + dx, y0 + blockIdx.y, z0 + blockIdx.z);
+    kind[i] = k;
+    bcid[i] = id;
+}
+
+// the loop of io/vtk.hpp:141-150: mask value 0 => the solid handler.  `mask` holds x-y planes of interior
+// cells; local plane z of this slab takes mask plane (z - mask_z_shift).
+__global__ void paint_mask_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ kind, uint16_t* __restrict__ bcid,
+                                  const Layout g, int z_lo, int mask_z_shift, uint8_t k, uint16_t id)
+{
+    const int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = 1 + blockIdx.y;
+    const int z = z_lo + blockIdx.z;
+    if (x > g.xl) return;
+    const size_t o = ((size_t) (z - mask_z_shift) * g.yl + (y - 1)) * g.xl + (x - 1);
+    if (!mask[o]) {
+        const int i = cell_at(g, x, y, z);
+        kind[i] = k;
+        bcid[i] = id;
+    }
+}
+
+// Domain::set_nonfluid_cells_nullcollide (domain.hpp:101-113, cell.hpp:75-92): interior cells without an
+// in-bounds fluid neighbour (the q loop includes the rest velocity, so fluid cells never qualify) take the
+// do-nothing handler.  Tagging never changes who is fluid, so it can be done in place.
+template <int Q>
+__global__ void tag_null_kernel(uint8_t* __restrict__ kind, const Layout g, int z_first, int zl_global,
+                                unsigned int* __restrict__ count)
+{
+    const Tables<Q>& T = tables<Q>();
+    const int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = 1 + blockIdx.y;
+    const int z = 1 + blockIdx.z;
+    if (x > g.xl) return;
+    const int i = cell_at(g, x, y, z);
+    if (kind[i] == K_FLUID) return;
+    for (int q = 0; q < Q; ++q) {
+        const int nx = x + T.c[q][0], ny = y + T.c[q][1], nz = z + T.c[q][2];
+        const int gz = nz + z_first - 1;
+        if (nx > 0 && nx < g.xl + 1 && ny > 0 && ny < g.yl + 1 && gz > 0 && gz < zl_global + 1
+            && kind[i + (T.c[q][2] * g.plane + T.c[q][1] * g.P + T.c[q][0])] == K_FLUID)
+            return;
+    }
+    if (kind[i] != K_NULL) atomicAdd(count, 1u);
+    kind[i] = K_NULL;
+}
+
+// a tagged cell keeps its former handler id: restore its kind from the table (used when the two lattices
+// start to differ and only one of them carries the tags)
+__global__ void untag_null_kernel(uint8_t* __restrict__ kind, const uint16_t* __restrict__ bcid,
+                                  const BcRec* __restrict__ bc, int n_bc, long long n)
+{
+    const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (kind[i] == K_NULL && bcid[i] < n_bc) kind[i] = (uint8_t) bc[bcid[i]].kind;
+}
+
+// Check of dense maps (reference idx order, planes [z0, z0+nz) of the slab) before they are accepted:
+// known kinds, handler ids inside the table and of the same kind, PERIODIC only on the ghost shell;
+// result[0] = min over offending cells of (dense index * 8 + reason)
+__global__ void validate_dense_kernel(const uint8_t* __restrict__ kind, const uint16_t* __restrict__ bcid,
+                                      const BcRec* __restrict__ bc, int n_bc, const Layout g, int z0,
+                                      unsigned long long* __restrict__ result)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int zz = blockIdx.z;
+    if (x > g.xl + 1) return;
+    const unsigned long long d = ((unsigned long long) zz * (g.yl + 2) + y) * (g.xl + 2) + x;
+    const int k = kind[d];
+    const int z = z0 + zz;
+    int why = 0;
+    if (k >= K_COUNT) why = 1;
+    else if (k >= K_NOSLIP && k <= K_PRESSURE) {
+        const int id = bcid[d];
+        if (id >= n_bc) why = 2;
+        else if (bc[id].kind != k) why = 3;
+    } else if (k == K_PERIODIC && x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1) why = 4;
+    if (why) atomicMin(result, (d + (unsigned long long) z0 * (g.yl + 2) * (g.xl + 2)) * 8ull + (unsigned long long) why);
+}
+
+// padded device maps -> dense (reference idx order), planes [z0, z0+nz).  report_former: cells tagged by
+// set_nonfluid_cells_nullcollide report their former handler's kind (see lbm_b200_tag_null_cells).
+__global__ void gather_maps_kernel(const uint8_t* __restrict__ kind, const uint16_t* __restrict__ bcid,
+                                   const BcRec* __restrict__ bc, int n_bc, uint8_t* __restrict__ kind_out,
+                                   uint16_t* __restrict__ bcid_out, const Layout g, int z0, int report_former)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int zz = blockIdx.z;
+    if (x > g.xl + 1) return;
+    const int i = cell_at(g, x, y, z0 + zz);
+    const long long d = ((long long) zz * (g.yl + 2) + y) * (g.xl + 2) + x;
+    int k = kind[i];
+    const int id = bcid[i];
+    if (report_former && k == K_NULL && id < n_bc) k = bc[id].kind;
+    if (kind_out) kind_out[d] = (uint8_t) k;
+    if (bcid_out) bcid_out[d] = (uint16_t) id;
 }
 
 // dense (reference idx order) byte/short maps -> padded device maps, planes [z0, z0+nz)
@@ -625,14 +874,19 @@ __global__ void equilibrium_kernel(const double* __restrict__ rho, const double*
 // Before sweep number n+1 a slab waits until both neighbours have completed n
 // sweeps: that orders "their halo stores landed" (read-after-write) as well as
 // "they no longer read the buffer we are about to overwrite" (write-after-read).
+// The epoch (sweeps this slab has completed since its peers were connected) lives in device memory and is
+// advanced by the signal kernel itself, so the wait / sweep / signal sequence of a step has no host-supplied
+// argument that changes from step to step and can be replayed from a CUDA graph.
 __global__ void halo_signal_kernel(unsigned long long* peer_flag_a, unsigned long long* peer_flag_b,
-                                   unsigned long long epoch, unsigned long long* scratch)
+                                   unsigned long long* my_epoch, unsigned long long* scratch)
 {
     // atomics are performed at the owning GPU's L2 (the point of coherence), so the value is visible
     // to the neighbour's poll as soon as the NVLink transaction lands.  The RETURNING form is used on
     // purpose: it is a round trip, so this kernel only retires once the neighbour really has the
     // value (a posted reduction may linger in the fabric until later traffic pushes it along).
     __threadfence_system();
+    const unsigned long long epoch = *my_epoch + 1;
+    *my_epoch = epoch;
     unsigned long long seen = 0;
     if (peer_flag_a) seen += atomicMax_system(peer_flag_a, epoch);
     if (peer_flag_b) seen += atomicMax_system(peer_flag_b, epoch);
@@ -640,11 +894,12 @@ __global__ void halo_signal_kernel(unsigned long long* peer_flag_a, unsigned lon
 }
 
 __global__ void halo_wait_kernel(unsigned long long* flag_a, unsigned long long* flag_b,
-                                 unsigned long long epoch, long long timeout_cycles, int* error_word,
-                                 unsigned long long* trace)
+                                 const unsigned long long* my_epoch, long long timeout_cycles, int* error_word,
+                                 volatile int* host_error_word, unsigned long long* trace, int trace_epochs)
 {
+    const unsigned long long epoch = *my_epoch;
     // optional trace (LBM_B200_HALO_TRACE): nanosecond timestamps of entry and exit per epoch
-    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[2 * epoch]));
+    if (trace && epoch < (unsigned long long) trace_epochs) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[2 * epoch]));
     const long long t0 = clock64();
     unsigned long long* flags[2] = { flag_a, flag_b };
     for (int k = 0; k < 2; ++k) {
@@ -655,13 +910,14 @@ __global__ void halo_wait_kernel(unsigned long long* flag_a, unsigned long long*
             if (v >= epoch) break;
             if (clock64() - t0 > timeout_cycles) {   // never hang the GPU on a lost neighbour
                 *error_word = 1;
+                if (host_error_word) *host_error_word = 1;   // pinned mirror: the host refuses further steps at once
                 return;
             }
             __nanosleep(100);
         }
     }
     __threadfence_system();
-    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[2 * epoch + 1]));
+    if (trace && epoch < (unsigned long long) trace_epochs) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[2 * epoch + 1]));
 }
 
 } // namespace lbmb200

@@ -202,9 +202,8 @@ class LocalSlabStack:
         self.slabs = [capi.Domain(Q, xl, yl, zl, tau, device=devices[r], z_first=zf, zl_local=nz, exact=exact)
                       for r, (zf, nz) in enumerate(self.ranges)]
         for (zf, nz), s in zip(self.ranges, self.slabs):
-            if fluid_mask is not None:
-                m = np.asarray(fluid_mask, dtype=np.uint8).reshape(zl, yl, xl)
-                s.set_fluid_mask(m[zf - 1:zf - 1 + nz])
+            if fluid_mask is not None:      # every slab also needs the rows of its neighbours' edge planes
+                s.set_fluid_mask_global(fluid_mask)
             if boxes:
                 s.set_boxes(boxes)
         for r in range(n_slabs):
@@ -227,9 +226,7 @@ class LocalSlabStack:
             s.upload(np.ascontiguousarray(f[zf - 1:zf + nz + 1]))
 
     def step(self, n=1):
-        for _ in range(n):
-            for s in self.slabs:
-                s.step(1)
+        capi.step_group(self.slabs, n)
 
     def sync(self):
         for s in self.slabs:

@@ -74,6 +74,8 @@ typedef struct {
                          /* cells flip solid/fluid on every swap()); 0 => set   */
                          /* on both fields like setBoundaryCondition does       */
     uint64_t steps;      /* number of stream(); swap(); collide(); iterations   */
+    uint64_t untimed;    /* the first `untimed` of those iterations are warm-up: */
+                         /* they run but are left out of orc_result.seconds      */
 } orc_case;
 
 typedef struct {

@@ -30,7 +30,7 @@ class Case(C.Structure):
                 ("xl", C.c_uint64), ("yl", C.c_uint64), ("zl", C.c_uint64),
                 ("tau", C.c_double), ("n_boxes", C.c_int32), ("periodic", C.c_int32),
                 ("boxes", C.POINTER(Box)), ("fluid_mask", C.c_void_p), ("f_init", C.c_void_p),
-                ("null_opt", C.c_int32), ("mask_literal", C.c_int32), ("steps", C.c_uint64)]
+                ("null_opt", C.c_int32), ("mask_literal", C.c_int32), ("steps", C.c_uint64), ("untimed", C.c_uint64)]
 
 
 class Result(C.Structure):
@@ -124,7 +124,7 @@ class Checker:
 
     # ---- whole-lattice run ----------------------------------------------------
     def run(self, Q, xl, yl, zl, tau, boxes, steps, *, f_init=None, fluid_mask=None, periodic=False,
-            null_opt=True, mask_literal=False, threads=None, want=("f", "rho", "u", "kind")):
+            null_opt=True, mask_literal=False, threads=None, untimed=0, want=("f", "rho", "u", "kind")):
         """Returns dict(f=[ncell,Q] AoS in Domain::idx order, rho=[zl,yl,xl], u=[zl,yl,xl,3],
         kind=[ncell], seconds)."""
         n_all = (xl + 2) * (yl + 2) * (zl + 2)
@@ -150,6 +150,7 @@ class Checker:
             assert fi.size == n_all * Q
             keep.append(fi); c.f_init = fi.ctypes.data
         c.null_opt, c.mask_literal, c.steps = int(bool(null_opt)), int(bool(mask_literal)), int(steps)
+        c.untimed = int(untimed)
         r = Result()
         out = {}
         if "f" in want:
@@ -180,6 +181,17 @@ def build_ref():
 
 
 _cache = {}
+
+
+def ref_fast():
+    """the reference's own headers again, compiled -O3 -mavx2 -mfma (FMA contraction allowed): the generous
+    CPU baseline of BASELINE.md; timing only, not bit-identical to the parity build.  None if not built."""
+    if "ref_fast" not in _cache:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_lbm_fast.so")
+        if not os.path.exists(path) and have_ref_sources():
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref_fast"])
+        _cache["ref_fast"] = Checker(path, "ref_") if os.path.exists(path) else None
+    return _cache["ref_fast"]
 
 
 def oracle():

@@ -1,4 +1,4 @@
-"""Scenario XML and config.cfg readers for the Python host side.
+"""Scenario XML and config.cfg readers (TEST PLUMBING: feeds the same scenario files to the CUDA path and the oracle).
 
 Python mirror of the reference's include/io/scenario.h:21-188 and include/io/configuration.h:68-121 (the C++
 mirrors live in include/lbm/io/): same element / attribute names, same defaults, same document-order semantics.
@@ -8,7 +8,7 @@ A scenario becomes the box list the C ABI takes (lbm_b200_set_boxes): one entry 
 import os
 import xml.etree.ElementTree as ET
 
-from . import capi
+from lbm_b200 import capi
 
 _CONDITIONS = {
     "noslip": capi.NOSLIP, "movingwall": capi.MOVINGWALL, "freeslip": capi.FREESLIP, "outflow": capi.OUTFLOW,

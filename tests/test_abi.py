@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built):
     for s in syms:
         assert hasattr(capi.lib, s), "missing export: " + s
     assert sorted(capi.SYMBOLS) == syms
-    assert capi.lib.lbm_b200_abi_version() == 1
+    assert capi.lib.lbm_b200_abi_version() == 2
 
 
 @pytest.mark.parametrize("Q", [15, 19, 27])

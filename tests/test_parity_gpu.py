@@ -240,7 +240,7 @@ def test_checkpoint_restart_continues_bit_exactly(tmp_path):
 def test_shipped_scenario_files_gpu_vs_oracle(xml, Q, steps):
     """the same scenario XML feeds both sides: GPU through lbm_b200.scenario, oracle through its box list"""
     import os
-    from lbm_b200 import scenario
+    import scenario_reader as scenario
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scenarios", xml)
     d, sc = scenario.domain_from_scenario(path, Q, TAU, exact=True)
     try:

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_shipped_scenarios_parse_to_the_expected_boxes(built):
-    from lbm_b200 import scenario
+    import scenario_reader as scenario
     sc = scenario.load_scenario(os.path.join(ROOT, "scenarios", "cavity64.xml"))
     assert (sc["name"], sc["xl"], sc["yl"], sc["zl"]) == ("Cavity64", 64, 64, 64)
     assert sc["boxes"] == O.cavity_boxes(64, 64, 64)
@@ -29,7 +29,7 @@ def test_shipped_scenarios_parse_to_the_expected_boxes(built):
 
 
 def test_reference_scenarios_parse_when_present(built):
-    from lbm_b200 import scenario
+    import scenario_reader as scenario
     base = "/root/reference/build/scenarios"
     if not os.path.isdir(base):
         pytest.skip("/root/reference absent")
@@ -54,7 +54,7 @@ def test_reference_scenarios_parse_when_present(built):
 
 
 def test_error_messages_follow_the_reference(built, tmp_path):
-    from lbm_b200 import scenario
+    import scenario_reader as scenario
     def bad(text, needle):
         p = tmp_path / "s.xml"
         p.write_text(text)
@@ -86,7 +86,7 @@ def test_error_messages_follow_the_reference(built, tmp_path):
 def test_reference_pipe_scenario_oracle_equals_compiled_reference(built):
     """the reference's own pipe fixture (250 x 54 x 54 mask, inflow/outflow): restatement == reference's code,
     with the mask tagged on both lattices and with the reference's literal collide-field-only tagging"""
-    from lbm_b200 import scenario
+    import scenario_reader as scenario
     ref = O.ref()
     if ref is None or not os.path.isdir("/root/reference/build/scenarios"):
         pytest.skip("needs /root/reference and oracle/_ref")

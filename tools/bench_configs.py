@@ -9,7 +9,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from lbm_b200 import capi, scenario  # noqa: E402
+from lbm_b200 import capi  # noqa: E402
+import scenario_reader as scenario  # noqa: E402
 import cases  # noqa: E402
 
 PEAK = 6539.2
