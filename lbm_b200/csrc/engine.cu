@@ -96,10 +96,7 @@ struct GeoLayer {
     uint32_t* bits = nullptr;
     int* inplace = nullptr;        // cells BGK-collided in place when this buffer is the DESTINATION
     int n_inplace = 0;
-    int* wall = nullptr;           // streamed cells with a non-zero link mask (steps whose SOURCE is this buffer), sorted
-    int n_wall = 0;
-    int wall_lo = 0, wall_hi = 0;  // how many of them lie in the first / last interior plane
-    double flagged = 0.0;          // fraction of the interior cells whose bit is set (wall cells + cells not streamed)
+    double solid = 0.0;            // fraction of the interior cells that are not streamed (steps whose SOURCE is this buffer)
 };
 
 struct lbm_b200 {
@@ -290,7 +287,6 @@ void free_layer(GeoLayer& L, bool maps)
         if (L.bits) cudaFree(L.bits);
     }
     if (L.inplace) cudaFree(L.inplace);
-    if (L.wall) cudaFree(L.wall);
     L = GeoLayer();
 }
 
@@ -380,39 +376,7 @@ int build_step_maps(lbm_b200* h, int src, int dst, bool* periodic_z)
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(h->stream));
     }
-    // the sorted list of streamed cells next to a wall: count per x-row, prefix sum, fill
-    if (S.wall) CU(cudaFree(S.wall));
-    S.wall = nullptr;
-    S.n_wall = S.wall_lo = S.wall_hi = 0;
-    S.flagged = (double) c[3] / ((double) g.xl * g.yl * g.zl);
-    const int rows = g.yl * g.zl;
-    DevBuf counts;
-    CU(cudaMalloc(&counts.p, (size_t) rows * sizeof(int)));
-    const int warps_per_block = 4;
-    const int row_blocks = (rows + warps_per_block - 1) / warps_per_block;
-    wall_count_kernel<<<row_blocks, 32 * warps_per_block, 0, h->stream>>>(S.mask, g, counts.as<int>());
-    h->launches++;
-    CU(cudaGetLastError());
-    std::vector<int> start(rows);
-    CU(cudaMemcpyAsync(start.data(), counts.p, (size_t) rows * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    long long total = 0;
-    for (int r = 0; r < rows; ++r) {
-        const int n = start[r];
-        start[r] = (int) total;
-        total += n;
-        if (r == g.yl - 1) S.wall_lo = (int) total;
-    }
-    S.wall_hi = (int) (total - (g.zl > 1 ? start[(size_t) (g.zl - 1) * g.yl] : 0));
-    S.n_wall = (int) total;
-    if (S.n_wall) {
-        CU(cudaMalloc(&S.wall, (size_t) S.n_wall * sizeof(int)));
-        CU(cudaMemcpyAsync(counts.p, start.data(), (size_t) rows * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        wall_fill_kernel<<<row_blocks, 32 * warps_per_block, 0, h->stream>>>(S.mask, g, counts.as<int>(), S.wall);
-        h->launches++;
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(h->stream));
-    }
+    S.solid = (double) c[3] / ((double) g.xl * g.yl * g.zl);
     return 0;
 }
 
@@ -499,9 +463,8 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step, int m
         constexpr int Q = decltype(Qc)::value;
         auto go = [&](auto Ex) {
             constexpr bool EX = decltype(Ex)::value;
-            if (mode == SWEEP_BULK) sweep_kernel<Q, EX, SWEEP_BULK><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
-            else if (mode == SWEEP_CHECKED) sweep_kernel<Q, EX, SWEEP_CHECKED><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
-            else sweep_kernel<Q, EX, SWEEP_INLINE><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+            if (mode == SWEEP_CHECKED) sweep_kernel<Q, EX, SWEEP_CHECKED><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+            else sweep_kernel<Q, EX, SWEEP_SPECULATIVE><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
         };
         if (h->exact) go(std::true_type{});
         else go(std::false_type{});
@@ -512,45 +475,18 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step, int m
     return 0;
 }
 
-// wall cells [begin, end) of the source layer's sorted list
-int launch_wall(lbm_b200* h, int begin, int end, bool with_peers)
-{
-    if (end <= begin) return 0;
-    SweepParams p{};
-    int gxy[2];
-    fill_sweep_params(h, p, 1, with_peers, 1, gxy);
-    const GeoLayer& S = h->layer[h->cur];
-    const int n = end - begin;
-    dispatch_q(h->Q, [&](auto Qc) {
-        constexpr int Q = decltype(Qc)::value;
-        if (h->exact) wall_kernel<Q, true><<<(n + 127) / 128, 128, 0, h->stream>>>(p, S.wall + begin, n);
-        else wall_kernel<Q, false><<<(n + 127) / 128, 128, 0, h->stream>>>(p, S.wall + begin, n);
-        return 0;
-    });
-    h->launches++;
-    CU(cudaGetLastError());
-    return 0;
-}
-
-// how the interior launch treats flagged cells for the current source layer
+// how a launch over whole planes learns which cells are bulk cells, for the current source layer
 int interior_mode(const lbm_b200* h)
 {
     if (h->sweep_mode >= 0) return h->sweep_mode;
     // large solid regions: look at the bit before pulling (see SWEEP_CHECKED)
-    return h->layer[h->cur].flagged > 0.10 ? SWEEP_CHECKED : SWEEP_BULK;
+    return h->layer[h->cur].solid > 0.10 ? SWEEP_CHECKED : SWEEP_SPECULATIVE;
 }
 
-// planes [z0, z0 + nz) in full: the sweep plus, unless it handles them inline, the wall cells of those planes
+// planes [z0, z0 + nz)
 int sweep_planes(lbm_b200* h, int z0, int nz, bool with_peers)
 {
-    if (nz <= 0) return 0;
-    const int mode = interior_mode(h);
-    TRY(launch_sweep(h, z0, nz, with_peers, 1, mode));
-    if (mode == SWEEP_INLINE) return 0;
-    const GeoLayer& S = h->layer[h->cur];
-    const int begin = z0 > 1 ? S.wall_lo : 0;
-    const int end = z0 + nz - 1 < h->g.zl ? S.n_wall - S.wall_hi : S.n_wall;
-    return launch_wall(h, begin, end, with_peers);
+    return launch_sweep(h, z0, nz, with_peers, 1, interior_mode(h));
 }
 
 // cells that are collided without being streamed (K1g), in the buffer that becomes the collide field
@@ -633,7 +569,7 @@ int enqueue_step(lbm_b200* h)
         // part in the hand-shake; the interior sweep that follows gives every neighbour a whole
         // step of slack before its next wait.
         TRY(halo_wait(h));
-        TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1, SWEEP_INLINE));
+        TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1, interior_mode(h)));
         TRY(halo_signal(h));
         TRY(sweep_planes(h, 2, h->g.zl - 2, false));
     } else {
@@ -842,7 +778,7 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
     h->z_first = (int) z_first;
     h->tau = tau;
     if (const char* e = getenv("LBM_B200_GRAPHS")) h->graph_mode = atoi(e);
-    if (const char* e = getenv("LBM_B200_SWEEP_MODE")) h->sweep_mode = std::max(-1, std::min(2, atoi(e)));
+    if (const char* e = getenv("LBM_B200_SWEEP_MODE")) h->sweep_mode = std::max(-1, std::min(1, atoi(e)));
     {
         double vel[27 * 3];
         lbm_b200_model(Q, vel, nullptr);
@@ -1779,8 +1715,8 @@ int lbm_b200_step_edges(lbm_b200_t* h)
     GUARD(h);
     if (h->edges_done) return fail(LBM_B200_ESTATE, "step_edges called twice");
     TRY(ready_to_step(h));
-    if (h->g.zl > 1) TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1, SWEEP_INLINE));
-    else TRY(launch_sweep(h, 1, 1, true, 1, SWEEP_INLINE));
+    if (h->g.zl > 1) TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1, interior_mode(h)));
+    else TRY(launch_sweep(h, 1, 1, true, 1, interior_mode(h)));
     h->edges_done = true;
     return 0;
 }

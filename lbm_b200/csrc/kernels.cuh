@@ -342,12 +342,43 @@ template <int Q> struct MinBlocks { static constexpr int value = Q == 15 ? LBM_M
 #define LBM_ST(ptr, v) (*(ptr) = (v))
 #endif
 
-// Collide, store, and hand slab-edge populations to the neighbour.  `f` holds the streamed populations.
+// Everything after the pull: replace the directions whose source is not fluid (link-wise boundary
+// values), collide, store, and hand slab-edge populations to the neighbour.  `f` holds the values
+// pulled for ALL directions; `m` is the cell's link mask (0 for bulk cells).  ONE code path: a cell
+// next to a wall patches f[] and falls through to the same collide + store instructions as a bulk
+// cell (a separate wall-cell path or launch was measured and is slower, profiles/r02_sweep_modes.txt).
 template <int Q, bool EXACT>
-__device__ __forceinline__ void collide_and_store(const SweepParams& p, double (&f)[Q], const int i, const int z)
+__device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q], const uint32_t m,
+                                            const int i, const int x, const int y, const int z)
 {
     using L = Lattice<Q>;
     const Layout& g = p.g;
+    if (m != 0) {
+        OwnMoments om;
+        om.have = false;
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            if (m & (1u << q)) {
+                const int s = i - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
+                const int k = p.kind[s];
+                if (k == K_PERIODIC) {
+                    const int sx = wrap1(x - L::cx(q), g.xl), sy = wrap1(y - L::cy(q), g.yl);
+                    const int sz = p.wrap_z ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
+                    f[q] = p.src[q * g.qstride + cell_at(g, sx, sy, sz)];
+                } else if (!p.first) {   // first step: the stored value already pulled is the answer
+                    f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, p.bc + p.bcid[s], om);
+                }
+            }
+        });
+        if (m & MASK_NOCOLLIDE) {   // streamed into a cell whose handler in the destination lattice is a boundary
+            static_for<Q>([&](auto I) {
+                constexpr int q = decltype(I)::value;
+                p.dstq[q][i] = f[q];
+            });
+            return;
+        }
+    }
+
     bgk_collide<Q, EXACT>(f, p.tau, p.omega);
 
     static_for<Q>([&](auto I) {
@@ -371,48 +402,14 @@ __device__ __forceinline__ void collide_and_store(const SweepParams& p, double (
     }
 }
 
-// Everything after the pull for a cell next to a wall: replace the directions whose source is not fluid
-// (link-wise boundary values), then collide and store.  `f` holds the values pulled speculatively for ALL
-// directions; `m` is the cell's link mask (non-zero).
-template <int Q, bool EXACT>
-__device__ __forceinline__ void finish_wall_cell(const SweepParams& p, double (&f)[Q], const uint32_t m,
-                                                 const int i, const int x, const int y, const int z)
-{
-    using L = Lattice<Q>;
-    const Layout& g = p.g;
-    OwnMoments om;
-    om.have = false;
-    static_for<Q>([&](auto I) {
-        constexpr int q = decltype(I)::value;
-        if (m & (1u << q)) {
-            const int s = i - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
-            const int k = p.kind[s];
-            if (k == K_PERIODIC) {
-                const int sx = wrap1(x - L::cx(q), g.xl), sy = wrap1(y - L::cy(q), g.yl);
-                const int sz = p.wrap_z ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
-                f[q] = p.src[q * g.qstride + cell_at(g, sx, sy, sz)];
-            } else if (!p.first) {   // first step: the stored value already pulled is the answer
-                f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, p.bc + p.bcid[s], om);
-            }
-        }
-    });
-    if (m & MASK_NOCOLLIDE) {   // streamed into a cell whose handler in the destination lattice is a boundary
-        static_for<Q>([&](auto I) {
-            constexpr int q = decltype(I)::value;
-            p.dstq[q][i] = f[q];
-        });
-        return;
-    }
-    collide_and_store<Q, EXACT>(p, f, i, z);
-}
-
-// How a sweep launch treats cells whose bit is set in `bits` (next to a wall, or not streamed at all):
-//   SWEEP_INLINE   handles them itself (link path inside the kernel); used for the two edge planes of a slab
-//   SWEEP_BULK     leaves them to wall_kernel; Q pulls and the bit are requested together (one DRAM round trip)
-//   SWEEP_CHECKED  leaves them to wall_kernel and looks at the bit BEFORE pulling: a flagged cell costs one
-//                  read of the (L2-resident) bit map instead of Q wasted pulls -- for geometries with large
-//                  solid regions (pipe.vtk: 44 % of the cells are solid)
-enum : int { SWEEP_INLINE = 0, SWEEP_BULK = 1, SWEEP_CHECKED = 2 };
+// How a sweep launch finds out whether its cell is a bulk cell:
+//   SWEEP_SPECULATIVE  the 1-bit map and the Q pulls are requested TOGETHER: every pull source of an interior
+//                      cell exists in memory (ghost shell), so the loads need not wait for the map -> one DRAM
+//                      round trip per cell instead of two dependent ones.  A cell that turns out not to be
+//                      streamed (solid) has pulled Q values for nothing.
+//   SWEEP_CHECKED      looks at the bit (L2-resident map) BEFORE pulling: a solid cell costs one map read instead
+//                      of Q wasted pulls -- for geometries with large solid regions (pipe.vtk: 44 % solid).
+enum : int { SWEEP_SPECULATIVE = 0, SWEEP_CHECKED = 1 };
 
 template <int Q, bool EXACT, int MODE>
 __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_kernel(const SweepParams p)
@@ -424,96 +421,25 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
     const int z = p.z0 + blockIdx.z * p.z_step;
     if (x > g.xl || y > g.yl) return;
     const int i = cell_at(g, x, y, z);
-    // The link bit and the Q pulled populations are requested TOGETHER: every pull source of an
-    // interior cell exists in memory (ghost shell), so the loads need not wait for the mask.  One
-    // DRAM round trip per cell instead of two dependent ones.  Bulk cells read 1/8 byte of map, not 4.
+    // Bulk cells read 1/8 byte of map, not 4.
     const uint32_t word = p.bits[i >> 5];
+    uint32_t m = 0;
     if constexpr (MODE == SWEEP_CHECKED) {
-        if ((word >> (i & 31)) & 1u) return;
+        if ((word >> (i & 31)) & 1u) {
+            m = p.mask[i];
+            if (m & MASK_SKIP) return;
+        }
     }
     double f[Q];
     static_for<Q>([&](auto I) {
         constexpr int q = decltype(I)::value;
         f[q] = LBM_LD(p.srcq[q] + i);
     });
-    if constexpr (MODE == SWEEP_INLINE) {
-        const uint32_t m = ((word >> (i & 31)) & 1u) ? p.mask[i] : 0u;
+    if constexpr (MODE == SWEEP_SPECULATIVE) {
+        m = ((word >> (i & 31)) & 1u) ? p.mask[i] : 0u;
         if (m & MASK_SKIP) return;
-        if (m != 0) {
-            finish_wall_cell<Q, EXACT>(p, f, m, i, x, y, z);
-            return;
-        }
-    } else if constexpr (MODE == SWEEP_BULK) {
-        if ((word >> (i & 31)) & 1u) return;
     }
-    collide_and_store<Q, EXACT>(p, f, i, z);
-}
-
-// K1w: the streamed cells next to a wall, one thread each, from the index list built at geometry commit
-// (sorted by cell index, so whole wall planes are still read and written in coalesced runs).  Every lane
-// takes the link path, which a sweep warp with a single wall cell would execute for one lane only.
-template <int Q, bool EXACT>
-__global__ void __launch_bounds__(128) wall_kernel(const SweepParams p, const int* __restrict__ cells, const int n)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const Layout& g = p.g;
-    const int i = cells[t];
-    const int c = i - X_SHIFT;
-    const int z = c / g.plane;
-    const int r = c - z * g.plane;
-    const int y = r / g.P;
-    const int x = r - y * g.P;
-    const uint32_t m = p.mask[i];
-    double f[Q];
-    static_for<Q>([&](auto I) {
-        constexpr int q = decltype(I)::value;
-        f[q] = p.srcq[q][i];
-    });
-    finish_wall_cell<Q, EXACT>(p, f, m, i, x, y, z);
-}
-
-// wall-cell list, pass 1: streamed cells with a non-zero link mask per x-row (one warp per row)
-__global__ void wall_count_kernel(const uint32_t* __restrict__ mask, const Layout g, int* __restrict__ row_count)
-{
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // over interior rows: (z-1)*yl + (y-1)
-    const int lane = threadIdx.x & 31;
-    if (row >= g.yl * g.zl) return;
-    const int z = 1 + row / g.yl, y = 1 + row % g.yl;
-    int n = 0;
-    for (int x0 = 1; x0 <= g.xl; x0 += 32) {
-        const int x = x0 + lane;
-        bool wall = false;
-        if (x <= g.xl) {
-            const uint32_t m = mask[cell_at(g, x, y, z)];
-            wall = m != 0 && !(m & MASK_SKIP);
-        }
-        n += __popc(__ballot_sync(0xffffffffu, wall));
-    }
-    if (lane == 0) row_count[row] = n;
-}
-// pass 2: row_start = exclusive prefix sum of row_count
-__global__ void wall_fill_kernel(const uint32_t* __restrict__ mask, const Layout g, const int* __restrict__ row_start,
-                                 int* __restrict__ cells)
-{
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= g.yl * g.zl) return;
-    const int z = 1 + row / g.yl, y = 1 + row % g.yl;
-    int base = row_start[row];
-    for (int x0 = 1; x0 <= g.xl; x0 += 32) {
-        const int x = x0 + lane;
-        bool wall = false;
-        int i = 0;
-        if (x <= g.xl) {
-            i = cell_at(g, x, y, z);
-            const uint32_t m = mask[i];
-            wall = m != 0 && !(m & MASK_SKIP);
-        }
-        const unsigned int b = __ballot_sync(0xffffffffu, wall);
-        if (wall) cells[base + __popc(b & ((1u << lane) - 1u))] = i;
-        base += __popc(b);
-    }
+    finish_cell<Q, EXACT>(p, f, m, i, x, y, z);
 }
 
 // K1g: ghost-shell cells that kept the fluid handler are BGK-collided in place in
@@ -661,7 +587,7 @@ __global__ void fill_weights_kernel(double* __restrict__ field, long long qstrid
 // counters[0] += cells that are collided in place without being streamed (fluid in the destination lattice,
 // but in the ghost shell or not fluid in the source lattice; domain.hpp:147-155 loops 0..l+1);
 // counters[1] |= 1 if a z ghost plane of the physical shell carries PERIODIC;
-// counters[3] += interior cells with a non-zero mask.
+// counters[3] += interior cells that are not streamed (solid in the source lattice).
 template <int Q>
 __global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const uint8_t* __restrict__ kind_dst,
                                   uint32_t* __restrict__ mask, uint32_t* __restrict__ bits, const Layout g,
@@ -687,7 +613,7 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const ui
     }
     mask[i] = m;
     if (m) atomicOr(&bits[i >> 5], 1u << (i & 31));   // bits zeroed by the caller
-    if (m && interior) atomicAdd(&counters[3], 1u);
+    if ((m & MASK_SKIP) && interior) atomicAdd(&counters[3], 1u);
     const bool neighbours_cell = (z == 0 && lo_interface) || (z == g.zl + 1 && hi_interface);
     if (!neighbours_cell) {
         if (!streamed && kind_dst[i] == K_FLUID) atomicAdd(&counters[0], 1u);
