@@ -206,6 +206,8 @@ int lbm_b200_sync(lbm_b200_t* h);
 int lbm_b200_elapsed_ms(lbm_b200_t* h, double* ms);
 /* kernels launched by this handle so far */
 int lbm_b200_launch_count(lbm_b200_t* h, uint64_t* n);
+/* how many of them were launches of the TMA-fed sweep (sweep_tma_kernel) */
+int lbm_b200_tma_launch_count(lbm_b200_t* h, uint64_t* n);
 uint64_t lbm_b200_steps_done(lbm_b200_t* h);
 
 /* n time steps of a whole stack of connected slabs (handles[0..n_handles), any devices) from one host
@@ -215,6 +217,13 @@ int lbm_b200_step_group(lbm_b200_t* const* handles, int n_handles, uint64_t n_st
 /* replay runs of steps from CUDA graphs (1 = always, 0 = never, -1 = automatic: small lattices, where
  * the launch overhead matters) */
 int lbm_b200_set_graphs(lbm_b200_t* h, int mode);
+/* which kernel sweeps whole planes (results are bit-identical either way; 1 = always where possible, 0 = never,
+ * -1 = automatic).  tma: the TMA-fed persistent kernel (one block per SM, shared-memory rings filled by
+ * cp.async.bulk.tensor) instead of one thread per cell pulling into registers -- an opt-in engine, never chosen
+ * automatically (it is slower, profiles/variants_r07_tma.txt).  checked: look at the 1-bit "not a bulk cell" map
+ * before pulling instead of together with the pulls -- automatic when more than 10 % of the interior cells are
+ * solid. */
+int lbm_b200_set_sweep_engine(lbm_b200_t* h, int tma, int checked);
 
 /* --- read-out (io/vtk.hpp:62-73): interior cells, z,y,x order --------------- */
 /* rho: xl*yl*zl_local doubles, u: 3x that (may each be NULL) */

@@ -33,7 +33,7 @@ SYMBOLS = [
     "lbm_b200_paint_mask", "lbm_b200_tag_null_cells",
     "lbm_b200_upload_populations", "lbm_b200_download_populations", "lbm_b200_init_equilibrium",
     "lbm_b200_save_checkpoint", "lbm_b200_load_checkpoint", "lbm_b200_upload_planes", "lbm_b200_download_planes",
-    "lbm_b200_step", "lbm_b200_step_group", "lbm_b200_set_graphs", "lbm_b200_sync", "lbm_b200_elapsed_ms", "lbm_b200_launch_count", "lbm_b200_steps_done",
+    "lbm_b200_step", "lbm_b200_step_group", "lbm_b200_set_graphs", "lbm_b200_set_sweep_engine", "lbm_b200_sync", "lbm_b200_elapsed_ms", "lbm_b200_launch_count", "lbm_b200_tma_launch_count", "lbm_b200_steps_done",
     "lbm_b200_macroscopic", "lbm_b200_macroscopic_begin", "lbm_b200_macroscopic_end", "lbm_b200_diagnostics",
     "lbm_b200_host_alloc", "lbm_b200_host_free", "lbm_b200_bind_host_thread",
     "lbm_b200_halo_layout", "lbm_b200_halo_plane", "lbm_b200_dst_buffer",
@@ -84,6 +84,7 @@ lib.lbm_b200_tag_null_cells.argtypes = [_H, C.c_int, C.POINTER(C.c_uint64)]
 lib.lbm_b200_get_kind.argtypes = [_H, C.c_void_p]
 lib.lbm_b200_step_group.argtypes = [C.POINTER(_H), C.c_int, C.c_uint64]
 lib.lbm_b200_set_graphs.argtypes = [_H, C.c_int]
+lib.lbm_b200_set_sweep_engine.argtypes = [_H, C.c_int, C.c_int]
 lib.lbm_b200_macroscopic_begin.argtypes = [_H, C.c_void_p, C.c_void_p]
 lib.lbm_b200_macroscopic_end.argtypes = [_H]
 lib.lbm_b200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
@@ -100,6 +101,7 @@ lib.lbm_b200_step.argtypes = [_H, C.c_uint64]
 lib.lbm_b200_sync.argtypes = [_H]
 lib.lbm_b200_elapsed_ms.argtypes = [_H, C.POINTER(C.c_double)]
 lib.lbm_b200_launch_count.argtypes = [_H, C.POINTER(C.c_uint64)]
+lib.lbm_b200_tma_launch_count.argtypes = [_H, C.POINTER(C.c_uint64)]
 lib.lbm_b200_macroscopic.argtypes = [_H, C.c_void_p, C.c_void_p]
 lib.lbm_b200_diagnostics.argtypes = [_H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
 lib.lbm_b200_halo_layout.argtypes = [_H, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
@@ -281,6 +283,9 @@ class Domain:
     def set_graphs(self, mode):
         _check(lib.lbm_b200_set_graphs(self._h, mode))
 
+    def set_sweep_engine(self, tma=-1, checked=-1):
+        _check(lib.lbm_b200_set_sweep_engine(self._h, tma, checked))
+
     def kind(self):
         k = np.empty(self.ncell, dtype=np.uint8)
         _check(lib.lbm_b200_get_kind(self._h, k.ctypes.data))
@@ -336,6 +341,11 @@ class Domain:
         n = C.c_uint64()
         _check(lib.lbm_b200_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def tma_launch_count(self):
+        n = C.c_uint64(0)
+        _check(lib.lbm_b200_tma_launch_count(self._h, C.byref(n)))
+        return int(n.value)
 
     def steps_done(self):
         return lib.lbm_b200_steps_done(self._h)

@@ -139,6 +139,7 @@ struct lbm_b200 {
     uint64_t steps = 0;
     uint64_t full_halo_at = ~0ull;   // time level for which neighbours pushed their full edge planes
     uint64_t launches = 0;
+    uint64_t tma_launches = 0;       // how many of them were sweep_tma_kernel
     bool edges_done = false;   // split-phase state
 
     // CUDA graphs of step runs (graph_mode: 1 always, 0 never, -1 automatic)
@@ -146,6 +147,7 @@ struct lbm_b200 {
     static constexpr int GRAPH_STEPS = 16;          // steps per graph (even: the buffer index returns)
     cudaGraphExec_t graph[2] = { nullptr, nullptr };   // [cur at entry]
     uint64_t graph_launches = 0;                    // kernel launches inside one graph
+    uint64_t graph_tma_launches = 0;
 
     // direct peer stores: [side]
     double* peer_f[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   // [side][buffer]
@@ -162,6 +164,12 @@ struct lbm_b200 {
     int* h_halo_error_dev = nullptr;                // its device address
     int clock_khz = 1965000;
     int sweep_mode = -1;                            // SWEEP_* for the interior launch; -1: chosen per geometry (LBM_B200_SWEEP_MODE)
+    // TMA-fed sweep (sweep_tma_kernel): 1 where possible, 0 / -1 never (LBM_B200_TMA) -- an opt-in engine
+    int tma_mode = -1;
+    int tma_bx = 0;                                 // box width chosen for this lattice (0: no tensor maps)
+    int sm_count = 148;
+    CUtensorMap tmap[2][2];                         // [buffer][shifted]: 4-D views (x, y, z, q) of the two lattices,
+                                                    // box bx x 256/bx, and (bx+2) x 256/bx for populations with c_x != 0
     long long pull_offset[27] = {};                 // c_z*plane + c_y*P + c_x per direction
     unsigned long long* d_trace = nullptr;         // LBM_B200_HALO_TRACE=<file prefix>: wait-kernel timestamps
     static constexpr int TRACE_EPOCHS = 8192;
@@ -475,6 +483,100 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step, int m
     return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 4-D tensor maps (element x of a padded row, y, z, q) over both lattices; boxes of bx (and bx+2) x 256/bx x 1 x 1 doubles
+int make_tensor_maps(lbm_b200* h)
+{
+    const Layout& g = h->g;
+    h->tma_bx = 0;
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return 0;                         // stays on sweep_kernel
+    int bx = 128;
+    while (bx > 32 && g.xl < bx - bx / 8) bx /= 2;   // narrow lattices take narrower, taller boxes
+    if (g.P < bx + 2 || g.yl + 2 < 256 / bx) return 0;
+    static const int promo = [] { const char* e = getenv("LBM_B200_TMA_L2PROMO"); return e ? atoi(e) : 0; }();
+    for (int b = 0; b < 4; ++b) {
+        const cuuint64_t dims[4] = { (cuuint64_t) g.P, (cuuint64_t) g.yl + 2, (cuuint64_t) g.zl + 2, (cuuint64_t) h->Q };
+        const cuuint64_t strides[3] = { (cuuint64_t) g.P * 8, (cuuint64_t) g.plane * 8, (cuuint64_t) g.qstride * 8 };
+        const cuuint32_t box[4] = { (cuuint32_t) (bx + 2 * (b & 1)), (cuuint32_t) (256 / bx), 1, 1 };
+        const cuuint32_t estr[4] = { 1, 1, 1, 1 };
+        const CUresult r = enc(&h->tmap[b >> 1][b & 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, h->f[b >> 1] + TMA_X0, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE),
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;
+    }
+    h->tma_bx = bx;
+    return 0;
+}
+
+// does this launch go through the TMA-fed kernel?
+bool tma_wanted(const lbm_b200* h, int nz, int mode)
+{
+    if (!h->tma_bx || h->tma_mode == 0 || h->first || mode != SWEEP_SPECULATIVE || nz <= 0) return false;
+    // opt-in only: measured at 0.42-0.51 of the HBM roofline against 0.946 for sweep_kernel, because 16-24 consumer
+    // warps cannot collide and store as many cells per second as 32 resident warps (profiles/variants_r07_tma.txt)
+    return h->tma_mode > 0;
+}
+
+template <int Q, bool EX, int BX>
+int launch_tma_one(lbm_b200* h, const SweepParams& p, int nz)
+{
+    using C = TmaCfg<Q>;
+    const Layout& g = h->g;
+    const int tiles_x = (g.xl + BX - 1) / BX, tiles_y = (g.yl + C::CELLS / BX - 1) / (C::CELLS / BX);
+    const long long n_tiles = (long long) tiles_x * tiles_y * nz;
+    static bool attr_set = false;     // per instantiation
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(sweep_tma_kernel<Q, EX, BX>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int blocks = (int) std::min<long long>(n_tiles, h->sm_count);
+    sweep_tma_kernel<Q, EX, BX><<<blocks, C::THREADS, C::SMEM_BYTES, h->stream>>>(p, h->tmap[h->cur][0], h->tmap[h->cur][1], tiles_x, tiles_y, nz);
+    return 0;
+}
+
+int launch_sweep_tma(lbm_b200* h, int z0, int nz, bool with_peers)
+{
+    SweepParams p{};
+    int gxy[2];
+    fill_sweep_params(h, p, z0, with_peers, 1, gxy);
+    int rc = dispatch_q(h->Q, [&](auto Qc) {
+        constexpr int Q = decltype(Qc)::value;
+        auto go = [&](auto Ex) {
+            constexpr bool EX = decltype(Ex)::value;
+            switch (h->tma_bx) {
+            case 128: return launch_tma_one<Q, EX, 128>(h, p, nz);
+            case 64: return launch_tma_one<Q, EX, 64>(h, p, nz);
+            default: return launch_tma_one<Q, EX, 32>(h, p, nz);
+            }
+        };
+        return h->exact ? go(std::true_type{}) : go(std::false_type{});
+    });
+    TRY(rc);
+    h->launches++;
+    h->tma_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // how a launch over whole planes learns which cells are bulk cells, for the current source layer
 int interior_mode(const lbm_b200* h)
 {
@@ -486,7 +588,9 @@ int interior_mode(const lbm_b200* h)
 // planes [z0, z0 + nz)
 int sweep_planes(lbm_b200* h, int z0, int nz, bool with_peers)
 {
-    return launch_sweep(h, z0, nz, with_peers, 1, interior_mode(h));
+    const int mode = interior_mode(h);
+    if (tma_wanted(h, nz, mode)) return launch_sweep_tma(h, z0, nz, with_peers);
+    return launch_sweep(h, z0, nz, with_peers, 1, mode);
 }
 
 // cells that are collided without being streamed (K1g), in the buffer that becomes the collide field
@@ -594,14 +698,16 @@ int run_graph(lbm_b200* h)
 {
     const int parity = h->cur;
     if (!h->graph[parity]) {
-        const uint64_t launches0 = h->launches, steps0 = h->steps;
+        const uint64_t launches0 = h->launches, steps0 = h->steps, tma0 = h->tma_launches;
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         int rc = 0;
         for (int s = 0; s < lbm_b200::GRAPH_STEPS && rc == 0; ++s) rc = enqueue_step(h);
         cudaError_t e = cudaStreamEndCapture(h->stream, &g);
         h->graph_launches = h->launches - launches0;
+        h->graph_tma_launches = h->tma_launches - tma0;
         h->launches = launches0;      // nothing has run yet
+        h->tma_launches = tma0;
         h->steps = steps0;
         if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
         if (e != cudaSuccess) return fail(LBM_B200_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -611,6 +717,7 @@ int run_graph(lbm_b200* h)
     }
     CU(cudaGraphLaunch(h->graph[parity], h->stream));
     h->launches += h->graph_launches;
+    h->tma_launches += h->graph_tma_launches;
     h->steps += lbm_b200::GRAPH_STEPS;
     h->materialized = false;
     return 0;
@@ -779,6 +886,7 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
     h->tau = tau;
     if (const char* e = getenv("LBM_B200_GRAPHS")) h->graph_mode = atoi(e);
     if (const char* e = getenv("LBM_B200_SWEEP_MODE")) h->sweep_mode = std::max(-1, std::min(1, atoi(e)));
+    if (const char* e = getenv("LBM_B200_TMA")) h->tma_mode = std::max(-1, std::min(1, atoi(e)));
     {
         double vel[27 * 3];
         lbm_b200_model(Q, vel, nullptr);
@@ -813,6 +921,11 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
         cudaGetLastError();
         h->clock_khz = 1965000;
     }
+    if (cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->sm_count <= 0) {
+        cudaGetLastError();
+        h->sm_count = 148;
+    }
+    make_tensor_maps(h);
     CUB(cudaMalloc(&h->d_halo_error, sizeof(int)));
     CUB(cudaMemset(h->d_halo_error, 0, sizeof(int)));
     CUB(cudaHostAlloc(&h->h_halo_error, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
@@ -957,6 +1070,14 @@ int lbm_b200_set_graphs(lbm_b200_t* h, int mode)
 {
     if (!h) return fail(LBM_B200_EINVAL, "null handle");
     h->graph_mode = mode < 0 ? -1 : (mode ? 1 : 0);
+    return 0;
+}
+int lbm_b200_set_sweep_engine(lbm_b200_t* h, int tma, int checked)
+{
+    if (!h) return fail(LBM_B200_EINVAL, "null handle");
+    h->tma_mode = tma < 0 ? -1 : (tma ? 1 : 0);
+    h->sweep_mode = checked < 0 ? -1 : (checked ? SWEEP_CHECKED : SWEEP_SPECULATIVE);
+    drop_graphs(h);
     return 0;
 }
 int lbm_b200_set_stream(lbm_b200_t* h, void* cuda_stream)
@@ -1498,6 +1619,12 @@ int lbm_b200_launch_count(lbm_b200_t* h, uint64_t* n)
 {
     if (!h || !n) return fail(LBM_B200_EINVAL, "null argument");
     *n = h->launches;
+    return 0;
+}
+int lbm_b200_tma_launch_count(lbm_b200_t* h, uint64_t* n)
+{
+    if (!h || !n) return fail(LBM_B200_EINVAL, "null argument");
+    *n = h->tma_launches;
     return 0;
 }
 uint64_t lbm_b200_steps_done(lbm_b200_t* h) { return h ? h->steps : 0; }

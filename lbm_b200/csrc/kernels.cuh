@@ -17,6 +17,7 @@
 // into element 0 of the next row's padding, which that row never uses.
 #pragma once
 #include <cstdint>
+#include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "lattice.cuh"
 
 namespace lbmb200 {
@@ -30,6 +31,9 @@ constexpr uint32_t MASK_SKIP = 0x80000000u;       // not streamed: not an interi
 constexpr uint32_t MASK_NOCOLLIDE = 0x40000000u;  // streamed, but the destination lattice's handler is not the fluid one
                                                   // (only when the two lattices carry different handlers, see GeoLayer)
 constexpr int X_SHIFT = 15;                   // element offset of x = 0 inside a row
+constexpr int TMA_X0 = X_SHIFT - 1;           // the tensor maps of the TMA-fed sweep view rows from this element on:
+                                              // 16-byte aligned, x = 0 .. xl+1 at coordinates 1 .. xl+2 of ONE row of
+                                              // pitch P (cells x > P-16 of a row live in the next row's padding)
 
 struct BcRec {          // one boundary handler object, device copy
     int kind;
@@ -440,6 +444,221 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
         if (m & MASK_SKIP) return;
     }
     finish_cell<Q, EXACT>(p, f, m, i, x, y, z);
+}
+
+// ---------------------------------------------------------------------------
+// K1t: the same sweep fed by the TMA engine -- an OPT-IN engine (lbm_b200_set_sweep_engine / LBM_B200_TMA=1),
+// bit-identical to sweep_kernel but slower: the load side alone streams 6.7 TB/s, but 16-24 consumer warps do
+// not collide and store as many cells per second as sweep_kernel's 32 resident warps (profiles/variants_r07_tma.txt).  sweep_kernel's bytes in flight are bought with resident
+// threads and land in registers (768-1024 threads x Q loads); a block spends part of its life computing,
+// storing and being replaced, during which its registers hold nothing in flight.  Here ONE persistent
+// block per SM keeps a ring of shared-memory stages (all ~220 KB of it) permanently in flight:
+//   producer warp   per tile and population one cp.async.bulk.tensor of a BX x BY box of the 4-D tensor
+//                   (x, y, z, q) over the source lattice; the pull offset is just the box origin
+//                   (x0 - c_x, y0 - c_y, z - c_z, q) -- the copy engine does the shifted, unaligned read
+//   consumer warps  wait for the stage, take their cell's Q values into registers, release the stage at
+//                   once (before colliding), then run the SAME finish_cell as sweep_kernel: link-wise
+//                   boundary values, BGK, Q coalesced 128-byte-aligned stores
+// Tiles are dealt round-robin (tile t -> block t mod gridDim), so at any moment the chip works on one
+// contiguous window of the lattice, like the hardware block scheduler does for sweep_kernel.
+// The engine only accepts boxes that start on a 16-byte boundary (measured: an odd fp64 start coordinate is an
+// illegal instruction, tools/selftest/tma_selftest.cu), so populations with c_x != 0 are fetched as a box that is
+// two elements wider and starts one element early; the consumer reads at offset +1.  No extra 32-byte sector
+// is touched by that: the wider box covers exactly the sectors the shifted row segment lives in.
+// Out-of-range box elements (x beyond the row pitch) are zero-filled by the engine; they are only ever
+// pull sources of flagged directions, which finish_cell replaces (never used while p.first is set).
+template <int Q> struct TmaCfg {
+    using L = Lattice<Q>;
+    static constexpr int CELLS = 256;                         // cells per tile = consumer threads per group
+    static constexpr int SLOT0 = CELLS * 8;                   // bytes of one population of a tile, c_x == 0
+    static constexpr int SLOT1 = SLOT0 + 128;                 // c_x != 0: (BX+2) x BY doubles, rounded up to 128 bytes
+    static constexpr int n_shifted()
+    {
+        int n = 0;
+        for (int q = 0; q < Q; ++q) n += L::cx(q) != 0;
+        return n;
+    }
+    static constexpr int slot_offset(int q)                   // bytes from the start of a stage
+    {
+        int o = 0;
+        for (int k = 0; k < q; ++k) o += L::cx(k) != 0 ? SLOT1 : SLOT0;
+        return o;
+    }
+    static constexpr int STAGE_BYTES = slot_offset(Q);
+    static constexpr int tx_bytes(int bx) { return (Q - n_shifted()) * SLOT0 + n_shifted() * (bx + 2) * (CELLS / bx) * 8; }
+#ifdef LBM_TMA_GROUPS
+    static constexpr int GROUPS = LBM_TMA_GROUPS;
+#else
+    static constexpr int GROUPS = 2;                          // consumer groups working on alternate tiles
+#endif
+    // every group owns its own ring of DEPTH stages (a barrier is only ever waited on by ONE group, which
+    // therefore can never be more than one phase ahead of it -- parity waits cannot alias)
+#ifdef LBM_TMA_DEPTH
+    static constexpr int DEPTH = LBM_TMA_DEPTH;
+#else
+    static constexpr int DEPTH = (227 * 1024 - 256) / STAGE_BYTES / GROUPS;
+#endif
+    static constexpr int STAGES = GROUPS * DEPTH;
+    static constexpr int WARPS_PER_GROUP = CELLS / 32;
+    static constexpr int CONSUMER_WARPS = GROUPS * WARPS_PER_GROUP;
+    // A cp.async.bulk.tensor costs the ISSUING WARP ~150 ns, whatever its size (tools/selftest/tma_stream.cu:
+    // one warp issuing 2 KB boxes feeds 2.0 TB/s chip-wide, 8 warps 6.0 TB/s, 19 warps 7.4 TB/s) -- so the
+    // populations of a tile are fetched by several producer warps in parallel, population q by warp q mod N.
+#ifdef LBM_TMA_PRODUCERS
+    static constexpr int PRODUCER_WARPS = LBM_TMA_PRODUCERS;
+#else
+    static constexpr int PRODUCER_WARPS = 8;
+#endif
+    static constexpr int THREADS = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
+    static_assert(SMEM_BYTES <= 227 * 1024, "stage ring exceeds the shared memory of an SM");
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int Q, bool EXACT, int BX>
+__global__ void __launch_bounds__(TmaCfg<Q>::THREADS, 1)
+sweep_tma_kernel(const SweepParams p, const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                 const int tiles_x, const int tiles_y, const int nz)
+{
+    using C = TmaCfg<Q>;
+    constexpr int BY = C::CELLS / BX;
+    constexpr int S = C::STAGES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t) S * C::STAGE_BYTES);
+    uint64_t* empty = full + S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Layout& g = p.g;
+    const unsigned int n_tiles = (unsigned int) tiles_x * tiles_y * nz;      // < 2^31 (checked by the host)
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, C::PRODUCER_WARPS < Q ? C::PRODUCER_WARPS : Q);
+            mbar_init(empty + s, C::WARPS_PER_GROUP);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= C::CONSUMER_WARPS) {
+        // ---- producers: one thread per producer warp feeds populations pw, pw + N, pw + 2N, ...
+        // (tmap0: BX x BY boxes, tmap1: (BX+2) x BY boxes for c_x != 0)
+        const int pw = warp - C::CONSUMER_WARPS;
+        if (lane != 0 || pw >= Q) return;
+        const Tables<Q>& T = tables<Q>();
+        // this warp's populations, their slots and box origins relative to the tile: fixed for the whole launch
+        constexpr int MAX_OPS = (Q + C::PRODUCER_WARPS - 1) / C::PRODUCER_WARPS;
+        int o_slot[MAX_OPS], o_x[MAX_OPS], o_y[MAX_OPS], o_z[MAX_OPS];
+        const CUtensorMap* o_map[MAX_OPS];
+        int my_bytes = 0;
+        #pragma unroll
+        for (int j = 0; j < MAX_OPS; ++j) {
+            const int q = pw + j * C::PRODUCER_WARPS;
+            o_slot[j] = 0; o_x[j] = o_y[j] = o_z[j] = 0; o_map[j] = &tmap0;
+            if (q < Q) {
+                for (int k = 0; k < q; ++k) o_slot[j] += T.c[k][0] != 0 ? C::SLOT1 : C::SLOT0;
+                const int cxq = T.c[q][0];
+                // box origin: x = 1 + tx*BX - c_x, one earlier if shifted; the tensor view starts TMA_X0 elements
+                // into a row, where x = -1 would be -> the origin is always an even element (16-byte aligned)
+                o_x[j] = 1 - cxq - (cxq != 0) + 1;
+                o_y[j] = 1 - T.c[q][1];
+                o_z[j] = p.z0 - T.c[q][2];
+#ifdef LBM_TMA_ONEMAP      /* timing experiment only: wrong results */
+                o_map[j] = &tmap0; o_x[j] = 2;
+                my_bytes += C::SLOT0;
+#else
+                o_map[j] = cxq != 0 ? &tmap1 : &tmap0;
+                my_bytes += cxq != 0 ? (BX + 2) * BY * 8 : C::SLOT0;
+#endif
+            }
+        }
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap1) : "memory");
+        int it = 0;
+        for (unsigned int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int k = it / C::GROUPS;                       // tile number inside its consumer group
+            const int s = (it % C::GROUPS) * C::DEPTH + k % C::DEPTH;
+            const uint32_t ph = (uint32_t) (k / C::DEPTH) & 1u;
+            const unsigned int r = t / (unsigned int) tiles_x;
+            const int tx = (int) (t - r * tiles_x);
+            const int tz = (int) (r / (unsigned int) tiles_y), ty = (int) (r - tz * tiles_y);
+            mbar_wait(empty + s, ph ^ 1u);           // a fresh barrier passes the wait on the opposite parity
+            mbar_expect_tx(full + s, my_bytes);
+            unsigned char* stage = smem_raw + (size_t) s * C::STAGE_BYTES;
+            #pragma unroll
+            for (int j = 0; j < MAX_OPS; ++j) {
+                const int q = pw + j * C::PRODUCER_WARPS;
+                if (q < Q) tma_load_4d(stage + o_slot[j], o_map[j], tx * BX + o_x[j], ty * BY + o_y[j], tz + o_z[j], q, full + s);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: group `grp` takes every GROUPS-th tile of this block
+    const int grp = warp / C::WARPS_PER_GROUP;
+    const int cell = (warp % C::WARPS_PER_GROUP) * 32 + lane;      // position inside the tile, x fastest
+    const int lx = cell % BX, ly = cell / BX;
+    int it = 0;
+    for (unsigned int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        if (it % C::GROUPS != grp) continue;
+        const int k = it / C::GROUPS;
+        const int s = grp * C::DEPTH + k % C::DEPTH;
+        const uint32_t ph = (uint32_t) (k / C::DEPTH) & 1u;
+        const unsigned int r = t / (unsigned int) tiles_x;
+        const int tx = (int) (t - r * tiles_x);
+        const int tz = (int) (r / (unsigned int) tiles_y), ty = (int) (r - tz * tiles_y);
+        const int x = 1 + tx * BX + lx, y = 1 + ty * BY + ly, z = p.z0 + tz;
+        const bool inside = x <= g.xl && y <= g.yl;
+        const int i = cell_at(g, x, y, z);
+        const uint32_t word = inside ? p.bits[i >> 5] : 0u;        // requested before the wait: off the critical path
+        mbar_wait(full + s, ph);
+        const unsigned char* st = smem_raw + (size_t) s * C::STAGE_BYTES;
+        double f[Q];
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            constexpr int off = C::slot_offset(q);
+            if constexpr (Lattice<Q>::cx(q) != 0) f[q] = reinterpret_cast<const double*>(st + off)[ly * (BX + 2) + lx + 1];
+            else f[q] = reinterpret_cast<const double*>(st + off)[cell];
+        });
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);                     // the stage can be refilled while we collide
+        if (!inside) continue;
+        const uint32_t m = ((word >> (i & 31)) & 1u) ? p.mask[i] : 0u;
+        if (m & MASK_SKIP) continue;
+#ifdef LBM_TMA_NOSTORE      /* timing experiment only: wrong results */
+        double acc = 0.0;
+        static_for<Q>([&](auto I) { acc += f[decltype(I)::value]; });
+        if (acc == 1.2345) p.dstq[0][i] = acc;
+#else
+        finish_cell<Q, EXACT>(p, f, m, i, x, y, z);
+#endif
+    }
 }
 
 // K1g: ghost-shell cells that kept the fluid handler are BGK-collided in place in
