@@ -261,6 +261,10 @@ int lbm_b200_halo_layout(lbm_b200_t* h, int* n_q, size_t* plane_bytes);
  * interior planes (c_z=+1 populations for UP, c_z=-1 for DOWN); receive planes
  * are the ghost planes (c_z=-1 populations arrive from UP, c_z=+1 from DOWN). */
 int lbm_b200_halo_plane(lbm_b200_t* h, int buffer, int side, int k, int recv, void** device_ptr);
+/* the same for ANY population q of the current collide field: the slab's edge plane on `side` (recv = 0) or the
+ * ghost plane behind it (recv = 1), plane_bytes each -- what an external transport moves for the read-back
+ * across slab cuts (every slab sends its Q edge planes to the neighbours, then calls lbm_b200_halo_pushed) */
+int lbm_b200_edge_plane(lbm_b200_t* h, int side, int q, int recv, void** device_ptr);
 /* physical buffer the step in flight writes (the one to exchange) */
 int lbm_b200_dst_buffer(lbm_b200_t* h);
 int lbm_b200_step_edges(lbm_b200_t* h);     /* sweep the two edge planes         */
@@ -274,7 +278,8 @@ int lbm_b200_connect(lbm_b200_t* h, int side, const void* blob);
 /* Read-back across slab cuts: every slab pushes ALL populations of its edge planes into the
  * neighbours' ghost planes (halo_push_all), the caller synchronises all slabs, then tells every slab
  * (halo_pushed); the following download / macroscopic then materialises boundary cells next to a
- * cut exactly like the reference's non-fluid pass (domain.hpp:157-165).  Needs connected peers. */
+ * cut exactly like the reference's non-fluid pass (domain.hpp:157-165).  halo_push_all needs connected peers;
+ * with an external transport move the planes of lbm_b200_edge_plane instead. */
 int lbm_b200_halo_push_all(lbm_b200_t* h);
 int lbm_b200_halo_pushed(lbm_b200_t* h);
 /* drop the peer mappings again: call on every slab (after a sync / barrier) before any is destroyed */

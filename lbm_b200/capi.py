@@ -36,7 +36,7 @@ SYMBOLS = [
     "lbm_b200_step", "lbm_b200_step_group", "lbm_b200_set_graphs", "lbm_b200_set_sweep_engine", "lbm_b200_sync", "lbm_b200_elapsed_ms", "lbm_b200_launch_count", "lbm_b200_tma_launch_count", "lbm_b200_steps_done",
     "lbm_b200_macroscopic", "lbm_b200_macroscopic_begin", "lbm_b200_macroscopic_end", "lbm_b200_diagnostics",
     "lbm_b200_host_alloc", "lbm_b200_host_free", "lbm_b200_bind_host_thread",
-    "lbm_b200_halo_layout", "lbm_b200_halo_plane", "lbm_b200_dst_buffer",
+    "lbm_b200_halo_layout", "lbm_b200_halo_plane", "lbm_b200_edge_plane", "lbm_b200_dst_buffer",
     "lbm_b200_step_edges", "lbm_b200_step_interior", "lbm_b200_step_finish",
     "lbm_b200_export", "lbm_b200_connect", "lbm_b200_connect_local", "lbm_b200_halo_push_all", "lbm_b200_halo_pushed",
     "lbm_b200_disconnect",
@@ -106,6 +106,7 @@ lib.lbm_b200_macroscopic.argtypes = [_H, C.c_void_p, C.c_void_p]
 lib.lbm_b200_diagnostics.argtypes = [_H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
 lib.lbm_b200_halo_layout.argtypes = [_H, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
 lib.lbm_b200_halo_plane.argtypes = [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+lib.lbm_b200_edge_plane.argtypes = [_H, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
 lib.lbm_b200_dst_buffer.argtypes = [_H]
 lib.lbm_b200_step_edges.argtypes = [_H]
 lib.lbm_b200_step_interior.argtypes = [_H]
@@ -381,6 +382,11 @@ class Domain:
     def halo_plane(self, buffer, side, k, recv):
         p = C.c_void_p()
         _check(lib.lbm_b200_halo_plane(self._h, buffer, side, k, int(recv), C.byref(p)))
+        return p.value
+
+    def edge_plane(self, side, q, recv):
+        p = C.c_void_p()
+        _check(lib.lbm_b200_edge_plane(self._h, side, q, int(recv), C.byref(p)))
         return p.value
 
     def dst_buffer(self):

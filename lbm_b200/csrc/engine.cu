@@ -471,7 +471,8 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step, int m
         constexpr int Q = decltype(Qc)::value;
         auto go = [&](auto Ex) {
             constexpr bool EX = decltype(Ex)::value;
-            if (mode == SWEEP_CHECKED) sweep_kernel<Q, EX, SWEEP_CHECKED><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+            if (mode == SWEEP_SPLIT) sweep_kernel<Q, EX, SWEEP_SPLIT><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+            else if (mode == SWEEP_CHECKED) sweep_kernel<Q, EX, SWEEP_CHECKED><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
             else sweep_kernel<Q, EX, SWEEP_SPECULATIVE><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
         };
         if (h->exact) go(std::true_type{});
@@ -508,8 +509,7 @@ int make_tensor_maps(lbm_b200* h)
     h->tma_bx = 0;
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return 0;                         // stays on sweep_kernel
-    int bx = 128;
-    while (bx > 32 && g.xl < bx - bx / 8) bx /= 2;   // narrow lattices take narrower, taller boxes
+    const int bx = g.xl >= 112 ? 128 : 32;          // narrow lattices take narrower, taller boxes
     if (g.P < bx + 2 || g.yl + 2 < 256 / bx) return 0;
     static const int promo = [] { const char* e = getenv("LBM_B200_TMA_L2PROMO"); return e ? atoi(e) : 0; }();
     for (int b = 0; b < 4; ++b) {
@@ -562,11 +562,7 @@ int launch_sweep_tma(lbm_b200* h, int z0, int nz, bool with_peers)
         constexpr int Q = decltype(Qc)::value;
         auto go = [&](auto Ex) {
             constexpr bool EX = decltype(Ex)::value;
-            switch (h->tma_bx) {
-            case 128: return launch_tma_one<Q, EX, 128>(h, p, nz);
-            case 64: return launch_tma_one<Q, EX, 64>(h, p, nz);
-            default: return launch_tma_one<Q, EX, 32>(h, p, nz);
-            }
+            return h->tma_bx == 128 ? launch_tma_one<Q, EX, 128>(h, p, nz) : launch_tma_one<Q, EX, 32>(h, p, nz);
         };
         return h->exact ? go(std::true_type{}) : go(std::false_type{});
     });
@@ -580,6 +576,7 @@ int launch_sweep_tma(lbm_b200* h, int z0, int nz, bool with_peers)
 // how a launch over whole planes learns which cells are bulk cells, for the current source layer
 int interior_mode(const lbm_b200* h)
 {
+    if (h->split) return SWEEP_SPLIT;          // MASK_NOCOLLIDE cells exist
     if (h->sweep_mode >= 0) return h->sweep_mode;
     // large solid regions: look at the bit before pulling (see SWEEP_CHECKED)
     return h->layer[h->cur].solid > 0.10 ? SWEEP_CHECKED : SWEEP_SPECULATIVE;
@@ -1836,6 +1833,16 @@ int lbm_b200_halo_plane(lbm_b200_t* h, int buffer, int side, int k, int recv, vo
 }
 
 int lbm_b200_dst_buffer(lbm_b200_t* h) { return h ? 1 - h->cur : -1; }
+
+int lbm_b200_edge_plane(lbm_b200_t* h, int side, int q, int recv, void** ptr)
+{
+    if (!h || !ptr) return fail(LBM_B200_EINVAL, "null argument");
+    if (side < 0 || side > 1 || q < 0 || q >= h->Q) return fail(LBM_B200_EINVAL, "bad side / population");
+    const Layout& g = h->g;
+    const int z = side == LBM_B200_UP ? (recv ? g.zl + 1 : g.zl) : (recv ? 0 : 1);
+    *ptr = h->f[h->cur] + (size_t) q * g.qstride + (size_t) z * g.plane + X_SHIFT;
+    return 0;
+}
 
 int lbm_b200_step_edges(lbm_b200_t* h)
 {

@@ -351,7 +351,7 @@ template <int Q> struct MinBlocks { static constexpr int value = Q == 15 ? LBM_M
 // pulled for ALL directions; `m` is the cell's link mask (0 for bulk cells).  ONE code path: a cell
 // next to a wall patches f[] and falls through to the same collide + store instructions as a bulk
 // cell (a separate wall-cell path or launch was measured and is slower, profiles/r02_sweep_modes.txt).
-template <int Q, bool EXACT>
+template <int Q, bool EXACT, bool SPLIT = false>
 __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q], const uint32_t m,
                                             const int i, const int x, const int y, const int z)
 {
@@ -374,7 +374,10 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
                 }
             }
         });
-        if (m & MASK_NOCOLLIDE) {   // streamed into a cell whose handler in the destination lattice is a boundary
+        // SPLIT (the two lattices carry different handlers, "literal" edits): a cell can be streamed into although
+        // its handler in the destination lattice is a boundary -- stored as streamed, not collided.  A separate
+        // instantiation: carrying this exit in the common kernel costs D3Q27 1.8 % (profiles/variants_r08_wall.txt)
+        if constexpr (SPLIT) if (m & MASK_NOCOLLIDE) {
             static_for<Q>([&](auto I) {
                 constexpr int q = decltype(I)::value;
                 p.dstq[q][i] = f[q];
@@ -413,7 +416,8 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
 //                      streamed (solid) has pulled Q values for nothing.
 //   SWEEP_CHECKED      looks at the bit (L2-resident map) BEFORE pulling: a solid cell costs one map read instead
 //                      of Q wasted pulls -- for geometries with large solid regions (pipe.vtk: 44 % solid).
-enum : int { SWEEP_SPECULATIVE = 0, SWEEP_CHECKED = 1 };
+//   SWEEP_SPLIT        SWEEP_CHECKED for lattices that carry different handlers (MASK_NOCOLLIDE cells exist)
+enum : int { SWEEP_SPECULATIVE = 0, SWEEP_CHECKED = 1, SWEEP_SPLIT = 2 };
 
 template <int Q, bool EXACT, int MODE>
 __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_kernel(const SweepParams p)
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
     // Bulk cells read 1/8 byte of map, not 4.
     const uint32_t word = p.bits[i >> 5];
     uint32_t m = 0;
-    if constexpr (MODE == SWEEP_CHECKED) {
+    if constexpr (MODE != SWEEP_SPECULATIVE) {
         if ((word >> (i & 31)) & 1u) {
             m = p.mask[i];
             if (m & MASK_SKIP) return;
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
         m = ((word >> (i & 31)) & 1u) ? p.mask[i] : 0u;
         if (m & MASK_SKIP) return;
     }
-    finish_cell<Q, EXACT>(p, f, m, i, x, y, z);
+    finish_cell<Q, EXACT, MODE == SWEEP_SPLIT>(p, f, m, i, x, y, z);
 }
 
 // ---------------------------------------------------------------------------

@@ -165,7 +165,8 @@ class SlabRunner:
         self.dom.sync()
 
     def prepare_readback(self):
-        """p2p transport only: full edge planes across the cuts before download()/macroscopic()"""
+        """full edge planes (all Q populations) across the cuts before download()/macroscopic(), so that boundary
+        cells next to a cut are materialised exactly like on one GPU"""
         import torch.distributed as dist
         self.dom.sync()
         if self.transport == "p2p":
@@ -173,6 +174,27 @@ class SlabRunner:
             self.dom.halo_push_all()
             self.dom.sync()
             dist.barrier(group=self.group)
+            self.dom.halo_pushed()
+        elif self.transport == "nccl":
+            torch = self.torch
+            n = self.dom.halo_layout()[1] // 8
+            keep, ops = [], []
+
+            def plane(side, q, recv):
+                arr = _DevArray(self.dom.edge_plane(side, q, recv), n)
+                keep.append(arr)
+                return torch.as_tensor(arr, device="cuda:%d" % self.device)
+            for q in range(self.dom.Q):
+                if self.up is not None:
+                    ops.append(dist.P2POp(dist.isend, plane(UP, q, False), self.up))
+                    ops.append(dist.P2POp(dist.irecv, plane(UP, q, True), self.up))
+                if self.down is not None:
+                    ops.append(dist.P2POp(dist.isend, plane(DOWN, q, False), self.down))
+                    ops.append(dist.P2POp(dist.irecv, plane(DOWN, q, True), self.down))
+            with torch.cuda.stream(self.stream):
+                for r in (dist.batch_isend_irecv(ops) if ops else []):
+                    r.wait()
+            self.dom.sync()
             self.dom.halo_pushed()
 
     def close(self):

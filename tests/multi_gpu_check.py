@@ -40,10 +40,8 @@ def main():
             wf = want["f"].reshape(zl + 2, -1, Q)[run.z_first:run.z_first + run.zl]
             fluid = (want["kind"] == O.FLUID).reshape(zl + 2, -1)[run.z_first:run.z_first + run.zl]
             got = f[1:run.zl + 1]
-            if exact and args.transport == "p2p":
-                good = np.array_equal(got, wf)          # obstacle cells next to the cuts included
-            elif exact:
-                good = np.array_equal(got[fluid], wf[fluid])
+            if exact:
+                good = np.array_equal(got, wf)          # obstacle cells next to the cuts included, either transport
             else:
                 good = float(np.max(np.abs(got[fluid] - wf[fluid]) / np.abs(wf[fluid]))) <= 1e-12
             flag = torch.tensor([1 if good else 0], device="cuda")
