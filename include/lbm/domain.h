@@ -79,9 +79,31 @@ class Domain
 
     struct Slab {
         lbm_b200_t* handle;
-        std::size_t z_first, zl_local;
+        std::size_t z_first, zl_local;      // first plane and number of planes along the split axis
     };
     std::vector<Slab> slabs;
+    // Split axis of a multi-GPU domain: z-slabs (x-y planes) normally; y-slabs (x-z planes) when the z extent is
+    // shorter than the number of GPUs (LBM_B200_SPLIT_AXIS=y|z overrides).  A y-slab's host arrays cover its own
+    // rows of every x-y plane, so the plane transfers below are stitched row-wise.
+    int split_axis { LBM_B200_AXIS_Z };
+    bool y_split() const { return split_axis == LBM_B200_AXIS_Y && slabs.size() > 1; }
+
+    // one x-y plane (ghost shell included) of per-cell items of `width` values: global <-> the rows a y-slab stores
+    template <typename T>
+    void rows_to_global(const Slab& s, const T* local, T* global, std::size_t width) const
+    {
+        const std::size_t row = (xl + 2) * width;
+        const bool first = s.z_first == 1, last = s.z_first + s.zl_local - 1 == yl;
+        for (std::size_t ly = first ? 0 : 1; ly <= s.zl_local + (last ? 1 : 0); ++ly)
+            std::memcpy(global + (s.z_first - 1 + ly) * row, local + ly * row, row * sizeof(T));
+    }
+    template <typename T>
+    void rows_to_local(const Slab& s, const T* global, T* local, std::size_t width) const
+    {
+        const std::size_t row = (xl + 2) * width;
+        std::memcpy(local, global + (s.z_first - 1) * row, (s.zl_local + 2) * row * sizeof(T));
+    }
+    std::size_t slab_plane_cells(const Slab& s) const { return (xl + 2) * (s.zl_local + 2); }
 
     // Handler bookkeeping.  The per-cell handler maps live on the device (one kind byte and one handler id
     // per cell and lattice); the host keeps the table id -> handler object (id 0 is the fluid operator)
@@ -197,9 +219,21 @@ class Domain
         const_cast<Domain*>(this)->push_geometry();
         hp.kind.resize(plane_cells());
         hp.id.resize(plane_cells());
-        const Slab& s = slabs[owner_of(z)];
-        device::check(lbm_b200_get_geometry_planes(s.handle, hp.kind.data(), hp.id.data(), z - (s.z_first - 1), 1),
-                "lbm_b200_get_geometry_planes");
+        if (y_split()) {
+            std::vector<std::uint8_t> k;
+            std::vector<std::uint16_t> id;
+            for (const Slab& s : slabs) {
+                k.resize(slab_plane_cells(s));
+                id.resize(slab_plane_cells(s));
+                device::check(lbm_b200_get_geometry_planes(s.handle, k.data(), id.data(), z, 1), "lbm_b200_get_geometry_planes");
+                rows_to_global(s, k.data(), hp.kind.data(), 1);
+                rows_to_global(s, id.data(), hp.id.data(), 1);
+            }
+        } else {
+            const Slab& s = slabs[owner_of(z)];
+            device::check(lbm_b200_get_geometry_planes(s.handle, hp.kind.data(), hp.id.data(), z - (s.z_first - 1), 1),
+                    "lbm_b200_get_geometry_planes");
+        }
         hp.valid = true;
         return hp;
     }
@@ -218,10 +252,19 @@ class Domain
         constexpr std::size_t Q = lattice_model::Q;
         if (pm.cells.empty()) pm.cells.assign(plane_cells(), Cell<lattice_model>(collision));
         pm.fetched.resize(plane_cells());
-        const Slab& s = slabs[owner_of(z)];
         std::vector<double> buf(plane_cells() * Q);
-        device::check(lbm_b200_download_planes(s.handle, buf.data(), LBM_B200_COLLIDE_FIELD, z - (s.z_first - 1), 1),
-                "lbm_b200_download_planes");
+        if (y_split()) {
+            std::vector<double> part;
+            for (const Slab& s : slabs) {
+                part.resize(slab_plane_cells(s) * Q);
+                device::check(lbm_b200_download_planes(s.handle, part.data(), LBM_B200_COLLIDE_FIELD, z, 1), "lbm_b200_download_planes");
+                rows_to_global(s, part.data(), buf.data(), Q);
+            }
+        } else {
+            const Slab& s = slabs[owner_of(z)];
+            device::check(lbm_b200_download_planes(s.handle, buf.data(), LBM_B200_COLLIDE_FIELD, z - (s.z_first - 1), 1),
+                    "lbm_b200_download_planes");
+        }
         const HandlerPlane& hp = fetch_handlers(z);
         for (std::size_t c = 0; c < plane_cells(); ++c) {
             std::memcpy(pm.cells[c].data(), buf.data() + c * Q, Q * sizeof(double));
@@ -256,9 +299,10 @@ class Domain
                     }
                     push_handlers();
                     for (auto& s : slabs)
-                        if (z + 1 >= s.z_first && z <= s.z_first + s.zl_local)
+                        if (!y_split() && z + 1 >= s.z_first && z <= s.z_first + s.zl_local)
                             device::check(lbm_b200_set_geometry_planes(s.handle, hp.kind.data(), hp.id.data(), z - (s.z_first - 1), 1, 1),
                                     "lbm_b200_set_geometry_planes");
+                    if (y_split()) throw std::logic_error("literal handler edits are limited to single-GPU domains");
                 } else {
                     for (auto c : changed) {
                         const std::uint64_t x = c % (xl + 2), y = c / (xl + 2);
@@ -273,10 +317,19 @@ class Domain
             }
             buf.resize(plane_cells() * Q);
             for (std::size_t c = 0; c < plane_cells(); ++c) std::memcpy(buf.data() + c * Q, pm.cells[c].data(), Q * sizeof(double));
-            for (auto& s : slabs)
-                if (z + 1 >= s.z_first && z <= s.z_first + s.zl_local)   // own plane or one of its two ghost planes
-                    device::check(lbm_b200_upload_planes(s.handle, buf.data(), LBM_B200_COLLIDE_FIELD, z - (s.z_first - 1), 1),
-                            "lbm_b200_upload_planes");
+            if (y_split()) {
+                std::vector<double> part;
+                for (auto& s : slabs) {                                   // every y-slab stores its rows of this plane
+                    part.resize(slab_plane_cells(s) * Q);
+                    rows_to_local(s, buf.data(), part.data(), Q);
+                    device::check(lbm_b200_upload_planes(s.handle, part.data(), LBM_B200_COLLIDE_FIELD, z, 1), "lbm_b200_upload_planes");
+                }
+            } else {
+                for (auto& s : slabs)
+                    if (z + 1 >= s.z_first && z <= s.z_first + s.zl_local)   // own plane or one of its two ghost planes
+                        device::check(lbm_b200_upload_planes(s.handle, buf.data(), LBM_B200_COLLIDE_FIELD, z - (s.z_first - 1), 1),
+                                "lbm_b200_upload_planes");
+            }
             pm.dirty = false;
         }
     }
@@ -310,15 +363,19 @@ public:
         planes.resize(zl + 2);
         handler_planes.resize(zl + 2);
         int n = device::gpus();
-        if (std::size_t(n) > zl) n = int(zl);
+        if (const char* e = std::getenv("LBM_B200_SPLIT_AXIS")) split_axis = (e[0] == 'y' || e[0] == 'Y') ? LBM_B200_AXIS_Y : LBM_B200_AXIS_Z;
+        else if (std::size_t(n) > zl && yl >= zl) split_axis = LBM_B200_AXIS_Y;      // too few x-y planes: cut along y
+        const std::size_t split_len = split_axis == LBM_B200_AXIS_Y ? yl : zl;
+        if (std::size_t(n) > split_len) n = int(split_len);
         const int visible = lbm_b200_device_count();
         if (visible < 1) throw std::runtime_error("Domain: no CUDA device visible; there is no CPU fallback");
         if (n > visible) throw std::runtime_error("Domain: " + std::to_string(n) + " GPUs requested, " + std::to_string(visible) + " visible");
         std::size_t z = 1;
         for (int r = 0; r < n; ++r) {
-            const std::size_t nz = zl / n + (std::size_t(r) < zl % n ? 1 : 0);
+            const std::size_t nz = split_len / n + (std::size_t(r) < split_len % n ? 1 : 0);
             lbm_b200_t* h = nullptr;
-            const int rc = lbm_b200_create_slab(&h, int(lattice_model::Q), xl, yl, zl, z, nz, bgk->relaxation_time(), n > 1 ? r : -1);
+            const int rc = lbm_b200_create_slab_axis(&h, int(lattice_model::Q), xl, yl, zl, n > 1 ? split_axis : LBM_B200_AXIS_Z,
+                    z, nz, bgk->relaxation_time(), n > 1 ? r : -1);
             if (rc != 0) {
                 const std::string msg = lbm_b200_last_error();
                 for (auto& s : slabs) lbm_b200_destroy(s.handle);
@@ -497,6 +554,22 @@ public:
             prepare_readback();
             readback_ready = true;
         }
+        if (y_split()) {
+            // a y-slab returns its rows of every plane: gather through a temporary and place them row-wise
+            std::vector<double> r, v;
+            for (auto& s : slabs) {
+                const std::size_t n = xl * s.zl_local * zl;
+                if (rho) r.resize(n);
+                if (u) v.resize(3 * n);
+                device::check(lbm_b200_macroscopic(s.handle, rho ? r.data() : nullptr, u ? v.data() : nullptr), "lbm_b200_macroscopic");
+                for (std::size_t z = 0; z < zl; ++z) {
+                    const std::size_t dst = (z * yl + (s.z_first - 1)) * xl, src = z * s.zl_local * xl, cnt = s.zl_local * xl;
+                    if (rho) std::memcpy(rho + dst, r.data() + src, cnt * sizeof(double));
+                    if (u) std::memcpy(u + 3 * dst, v.data() + 3 * src, 3 * cnt * sizeof(double));
+                }
+            }
+            return;
+        }
         for (auto& s : slabs) {
             const std::size_t off = (s.z_first - 1) * xl * yl;
             device::check(lbm_b200_macroscopic(s.handle, rho ? rho + off : nullptr, u ? u + 3 * off : nullptr),
@@ -516,6 +589,10 @@ public:
             prepare_readback();
             readback_ready = true;
         }
+        if (y_split()) {                 // rows are interleaved in the output: no asynchronous form, read out now
+            macroscopic(rho, u);
+            return;
+        }
         for (auto& s : slabs) {
             const std::size_t off = (s.z_first - 1) * xl * yl;
             device::check(lbm_b200_macroscopic_begin(s.handle, rho ? rho + off : nullptr, u ? u + 3 * off : nullptr),
@@ -524,8 +601,10 @@ public:
     }
     auto macroscopic_end() const -> void
     {
+        if (y_split()) return;
         for (auto& s : slabs) device::check(lbm_b200_macroscopic_end(s.handle), "lbm_b200_macroscopic_end");
     }
+    auto split_axis_name() const -> const char* { return y_split() ? "y" : "z"; }
     auto gpu_count() const -> std::size_t { return slabs.size(); }
     auto timesteps_done() const -> std::uint64_t { return steps_done; }
     auto slab_handle(std::size_t i) const -> lbm_b200_t* { return slabs.at(i).handle; }

@@ -117,6 +117,14 @@ int lbm_b200_create(lbm_b200_t** h, int Q, uint64_t xl, uint64_t yl, uint64_t zl
  * ghost plane on each side. */
 int lbm_b200_create_slab(lbm_b200_t** h, int Q, uint64_t xl, uint64_t yl, uint64_t zl_global,
                          uint64_t z_first, uint64_t zl_local, double tau, int device);
+/* The same for either split axis: (xl, yl, zl) is the GLOBAL domain, the handle owns the planes first ..
+ * first+local-1 (1-based) of `axis`: LBM_B200_AXIS_Z = x-y planes (z-slabs, as above), LBM_B200_AXIS_Y = x-z planes
+ * (y-slabs: for domains whose z extent is shorter than the number of GPUs, or flat ones such as the reference's
+ * shearflow scenario, 8 x 8 x 20).  A y-slab stores y as the slowest index, so its planes are contiguous and every
+ * halo function below works unchanged; its host arrays use the local lengths (xl, local, zl) in Domain::idx order. */
+enum { LBM_B200_AXIS_Y = 1, LBM_B200_AXIS_Z = 2 };
+int lbm_b200_create_slab_axis(lbm_b200_t** h, int Q, uint64_t xl, uint64_t yl, uint64_t zl, int axis,
+                              uint64_t first, uint64_t local, double tau, int device);
 int lbm_b200_destroy(lbm_b200_t* h);
 
 int lbm_b200_set_arithmetic(lbm_b200_t* h, int mode);

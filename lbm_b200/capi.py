@@ -19,13 +19,14 @@ FAST, EXACT = 0, 1
 AOS, SOA = 0, 1
 COLLIDE_FIELD, STREAM_FIELD = 0, 1
 DOWN, UP = 0, 1
+AXIS_Y, AXIS_Z = 1, 2
 EXPORT_BYTES = 256
 
 # every symbol include/lbm_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "lbm_b200_last_error", "lbm_b200_abi_version", "lbm_b200_device_count",
     "lbm_b200_model", "lbm_b200_model_inv", "lbm_b200_model_velocity_index",
-    "lbm_b200_create", "lbm_b200_create_slab", "lbm_b200_destroy",
+    "lbm_b200_create", "lbm_b200_create_slab", "lbm_b200_create_slab_axis", "lbm_b200_destroy",
     "lbm_b200_set_arithmetic", "lbm_b200_set_tau", "lbm_b200_set_stream",
     "lbm_b200_set_handlers", "lbm_b200_paint_boxes", "lbm_b200_set_boxes", "lbm_b200_set_geometry",
     "lbm_b200_set_geometry_planes", "lbm_b200_get_geometry_planes", "lbm_b200_get_kind",
@@ -66,6 +67,8 @@ lib.lbm_b200_model.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
 lib.lbm_b200_create.argtypes = [C.POINTER(_H), C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_int]
 lib.lbm_b200_create_slab.argtypes = [C.POINTER(_H), C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                      C.c_uint64, C.c_double, C.c_int]
+lib.lbm_b200_create_slab_axis.argtypes = [C.POINTER(_H), C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64,
+                                          C.c_uint64, C.c_double, C.c_int]
 lib.lbm_b200_destroy.argtypes = [_H]
 lib.lbm_b200_set_arithmetic.argtypes = [_H, C.c_int]
 lib.lbm_b200_set_tau.argtypes = [_H, C.c_double]
@@ -179,18 +182,25 @@ class Domain:
 
     Domain(Q, xl, yl, zl, tau)                        whole domain
     Domain(Q, xl, yl, zl_global, tau, z_first=, zl_local=)   one z-slab
+    Domain(Q, xl, yl_global, zl, tau, axis=AXIS_Y, z_first=, zl_local=)   one y-slab: rows z_first .. z_first+zl_local-1
+    xl, yl, zl of the object are the LOCAL lengths (what its host arrays use); yl_global / zl_global the domain's.
     """
 
-    def __init__(self, Q, xl, yl, zl, tau, device=-1, z_first=None, zl_local=None, exact=False):
+    def __init__(self, Q, xl, yl, zl, tau, device=-1, z_first=None, zl_local=None, exact=False, axis=AXIS_Z):
         self._h = _H()
-        self.Q, self.xl, self.yl, self.zl_global, self.tau = Q, xl, yl, zl, tau
+        self.Q, self.xl, self.yl, self.zl, self.tau, self.axis = Q, xl, yl, zl, tau, axis
+        self.yl_global, self.zl_global = yl, zl
         if z_first is None:
-            self.z_first, self.zl = 1, zl
+            self.z_first = 1
             _check(lib.lbm_b200_create(C.byref(self._h), Q, xl, yl, zl, tau, device))
         else:
-            self.z_first, self.zl = z_first, zl_local
-            _check(lib.lbm_b200_create_slab(C.byref(self._h), Q, xl, yl, zl, z_first, zl_local, tau, device))
-        self.ncell = (xl + 2) * (yl + 2) * (self.zl + 2)
+            self.z_first = z_first
+            if axis == AXIS_Y:
+                self.yl = zl_local
+            else:
+                self.zl = zl_local
+            _check(lib.lbm_b200_create_slab_axis(C.byref(self._h), Q, xl, yl, zl, axis, z_first, zl_local, tau, device))
+        self.ncell = (xl + 2) * (self.yl + 2) * (self.zl + 2)
         if exact:
             self.set_arithmetic(EXACT)
 
@@ -273,7 +283,7 @@ class Domain:
     def set_fluid_mask_global(self, mask, literal=False):
         """mask of the WHOLE domain; a slab picks its planes and its neighbours' edge planes"""
         m = np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
-        assert m.size == self.xl * self.yl * self.zl_global
+        assert m.size == self.xl * self.yl_global * self.zl_global
         _check(lib.lbm_b200_set_fluid_mask_global(self._h, m.ctypes.data, int(literal)))
 
     def tag_null_cells(self, literal=False):

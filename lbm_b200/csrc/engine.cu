@@ -103,8 +103,11 @@ struct lbm_b200 {
     int Q = 0;
     int device = 0;
     Layout g{};
+    // The split ("slow") axis of a slab is z (axis 2, planes = x-y planes) or y (axis 1, planes = x-z planes);
+    // zl_global / z_first are the global length of THAT axis and the global index of the slab's local plane 1.
+    int axis = 2;
     int zl_global = 0;
-    int z_first = 1;           // global index of local plane 1
+    int z_first = 1;
     double tau = 1.0;
     int exact = 0;
 
@@ -179,8 +182,11 @@ struct lbm_b200 {
     size_t map_elems() const { return (size_t) g.qstride; }
     size_t bits_words() const { return map_elems() / 32 + 2; }
     bool lo_interface() const { return z_first != 1; }
-    bool hi_interface() const { return z_first + g.zl - 1 != zl_global; }
-    bool is_slab() const { return g.zl != zl_global; }
+    int nslow() const { return n_slow(g); }
+    bool hi_interface() const { return z_first + nslow() - 1 != zl_global; }
+    bool is_slab() const { return nslow() != zl_global; }
+    int yl_global() const { return axis == 1 ? zl_global : g.yl; }      // logical global lengths
+    int zl_global_z() const { return axis == 1 ? g.zl : zl_global; }
 };
 
 namespace {
@@ -408,7 +414,7 @@ int commit_geometry(lbm_b200* h)
     if (periodic_z && h->is_slab()) {
         // closed by a ring of slabs instead: the first and the last slab must be each other's neighbours
         h->ring_lo = h->z_first == 1;
-        h->ring_hi = h->z_first + g.zl - 1 == h->zl_global;
+        h->ring_hi = h->z_first + h->nslow() - 1 == h->zl_global;
         periodic_z = false;
     }
     h->wrap_z = periodic_z ? 1 : 0;
@@ -457,7 +463,7 @@ void fill_sweep_params(lbm_b200* h, SweepParams& p, int z0, bool with_peers, int
     }
     const int bx = 1 << shift, by = LBM_SWEEP_THREADS >> shift;
     grid_xy[0] = (g.xl + bx - 1) / bx;
-    grid_xy[1] = (g.yl + by - 1) / by;
+    grid_xy[1] = (n_mid(g) + by - 1) / by;
 }
 
 int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step, int mode)
@@ -510,7 +516,7 @@ int make_tensor_maps(lbm_b200* h)
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return 0;                         // stays on sweep_kernel
     const int bx = g.xl >= 112 ? 128 : 32;          // narrow lattices take narrower, taller boxes
-    if (g.P < bx + 2 || g.yl + 2 < 256 / bx) return 0;
+    if (g.swap || g.P < bx + 2 || g.yl + 2 < 256 / bx) return 0;      // (z-slabs only)
     static const int promo = [] { const char* e = getenv("LBM_B200_TMA_L2PROMO"); return e ? atoi(e) : 0; }();
     for (int b = 0; b < 4; ++b) {
         const cuuint64_t dims[4] = { (cuuint64_t) g.P, (cuuint64_t) g.yl + 2, (cuuint64_t) g.zl + 2, (cuuint64_t) h->Q };
@@ -569,6 +575,36 @@ int launch_sweep_tma(lbm_b200* h, int z0, int nz, bool with_peers)
     TRY(rc);
     h->launches++;
     h->tma_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// CUDA loads kernels lazily, on their first launch, and a load may have to wait for the device to drain.  Inside
+// the time loop of a multi-slab run that is a deadlock: slab A's wait kernel spins for slab B's signal while the
+// host is stuck loading the kernel variant slab B launches for the first time (seen with y-slabs whose solid
+// fraction selects SWEEP_CHECKED for some slabs only; it ends with the hand-shake timeout).  So everything that
+// can be launched between two synchronisations is loaded when the handle is created.
+int preload_step_kernels(int Q)
+{
+    cudaFuncAttributes a;
+    dispatch_q(Q, [&](auto Qc) {
+        constexpr int QQ = decltype(Qc)::value;
+        cudaFuncGetAttributes(&a, sweep_kernel<QQ, false, SWEEP_SPECULATIVE>);
+        cudaFuncGetAttributes(&a, sweep_kernel<QQ, false, SWEEP_CHECKED>);
+        cudaFuncGetAttributes(&a, sweep_kernel<QQ, false, SWEEP_SPLIT>);
+        cudaFuncGetAttributes(&a, sweep_kernel<QQ, true, SWEEP_SPECULATIVE>);
+        cudaFuncGetAttributes(&a, sweep_kernel<QQ, true, SWEEP_CHECKED>);
+        cudaFuncGetAttributes(&a, sweep_kernel<QQ, true, SWEEP_SPLIT>);
+        cudaFuncGetAttributes(&a, ghost_fluid_kernel<QQ, false>);
+        cudaFuncGetAttributes(&a, ghost_fluid_kernel<QQ, true>);
+        cudaFuncGetAttributes(&a, sweep_tma_kernel<QQ, false, 128>);
+        cudaFuncGetAttributes(&a, sweep_tma_kernel<QQ, true, 128>);
+        cudaFuncGetAttributes(&a, sweep_tma_kernel<QQ, false, 32>);
+        cudaFuncGetAttributes(&a, sweep_tma_kernel<QQ, true, 32>);
+        return 0;
+    });
+    cudaFuncGetAttributes(&a, halo_wait_kernel);
+    cudaFuncGetAttributes(&a, halo_signal_kernel);
     CU(cudaGetLastError());
     return 0;
 }
@@ -665,17 +701,18 @@ void finish_step(lbm_b200* h)
 // the launches of one time step on h->stream
 int enqueue_step(lbm_b200* h)
 {
-    if (has_peers(h) && h->g.zl >= 3) {
+    const int ns = h->nslow();
+    if (has_peers(h) && ns >= 3) {
         // Only the two edge planes read ghost planes and feed the neighbours, so only they take
         // part in the hand-shake; the interior sweep that follows gives every neighbour a whole
         // step of slack before its next wait.
         TRY(halo_wait(h));
-        TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1, interior_mode(h)));
+        TRY(launch_sweep(h, 1, 2, true, ns - 1, interior_mode(h)));
         TRY(halo_signal(h));
-        TRY(sweep_planes(h, 2, h->g.zl - 2, false));
+        TRY(sweep_planes(h, 2, ns - 2, false));
     } else {
         TRY(halo_wait(h));
-        TRY(sweep_planes(h, 1, h->g.zl, true));
+        TRY(sweep_planes(h, 1, ns, true));
         TRY(halo_signal(h));
     }
     TRY(launch_inplace(h));
@@ -783,15 +820,17 @@ int before_geometry_change(lbm_b200* h)
 int paint_box(lbm_b200* h, const LayerSel& sel, const uint64_t* e, int kind, uint16_t id)
 {
     const Layout& g = h->g;
-    const long long zoff = h->z_first - 1;   // local z = global z - zoff
-    const long long lz0 = std::max<long long>((long long) e[4] - zoff, 0);
-    const long long lz1 = std::min<long long>((long long) e[5] - zoff, g.zl + 1);
-    if (lz0 > lz1) return 0;
-    const int nx = (int) (e[1] - e[0] + 1), ny = (int) (e[3] - e[2] + 1), nz = (int) (lz1 - lz0 + 1);
+    const long long off = h->z_first - 1;    // along the split axis: local index = global index - off
+    const int a = h->axis == 1 ? 2 : 4;      // position of that axis' extent inside the box
+    long long lo[3] = { (long long) e[0], (long long) e[2], (long long) e[4] }, hi[3] = { (long long) e[1], (long long) e[3], (long long) e[5] };
+    lo[a / 2] = std::max<long long>((long long) e[a] - off, 0);
+    hi[a / 2] = std::min<long long>((long long) e[a + 1] - off, h->nslow() + 1);
+    if (lo[a / 2] > hi[a / 2]) return 0;
+    const int nx = (int) (hi[0] - lo[0] + 1), ny = (int) (hi[1] - lo[1] + 1), nz = (int) (hi[2] - lo[2] + 1);
     const int threads = nx >= 128 ? 128 : 32;
     dim3 grid((nx + threads - 1) / threads, ny, nz);
     for (int l = 0; l < sel.n; ++l) {
-        paint_box_kernel<<<grid, threads, 0, h->stream>>>(sel.l[l]->kind, sel.l[l]->bcid, g, (int) e[0], (int) e[2], (int) lz0, nx, ny, (uint8_t) kind, id);
+        paint_box_kernel<<<grid, threads, 0, h->stream>>>(sel.l[l]->kind, sel.l[l]->bcid, g, (int) lo[0], (int) lo[1], (int) lo[2], nx, ny, (uint8_t) kind, id);
         h->launches++;
     }
     CU(cudaGetLastError());
@@ -803,7 +842,7 @@ int check_box(const lbm_b200* h, const uint64_t* e, int b)
     const Layout& g = h->g;
     // the reference asserts these (domain.hpp:180-181)
     if (!(e[1] >= e[0] && e[3] >= e[2] && e[5] >= e[4])) return fail(LBM_B200_EINVAL, "box %d: end before begin", b);
-    if (!(e[1] < (uint64_t) g.xl + 2 && e[3] < (uint64_t) g.yl + 2 && e[5] < (uint64_t) h->zl_global + 2))
+    if (!(e[1] < (uint64_t) g.xl + 2 && e[3] < (uint64_t) h->yl_global() + 2 && e[5] < (uint64_t) h->zl_global_z() + 2))
         return fail(LBM_B200_EINVAL, "box %d: extent outside the domain", b);
     return 0;
 }
@@ -845,21 +884,25 @@ int upload_map_planes(lbm_b200* h, const uint8_t* kind, const uint16_t* bc_id, i
     return 0;
 }
 
-int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl_global, uint64_t z_first,
+// (xl, yl_all, zl_all): the GLOBAL domain; the handle owns planes [first, first + local) of `axis` (1 = y, 2 = z)
+int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl_all, uint64_t zl_all, int axis, uint64_t z_first,
                   uint64_t zl_local, double tau, int device)
 {
     if (!out) return fail(LBM_B200_EINVAL, "null output pointer");
     *out = nullptr;
     if (Q != 15 && Q != 19 && Q != 27) return fail(LBM_B200_EINVAL, "Q must be 15, 19 or 27 (got %d)", Q);
-    if (xl == 0 || yl == 0 || zl_global == 0 || zl_local == 0)
+    if (axis != 1 && axis != 2) return fail(LBM_B200_EINVAL, "split axis must be 1 (y) or 2 (z)");
+    const uint64_t zl_global = axis == 1 ? yl_all : zl_all;          // length of the split axis
+    if (xl == 0 || yl_all == 0 || zl_all == 0 || zl_local == 0)
         return fail(LBM_B200_EINVAL, "domain lengths must be positive");
     if (z_first < 1 || z_first + zl_local - 1 > zl_global)
         return fail(LBM_B200_EINVAL, "slab [%llu, %llu] outside 1..%llu", (unsigned long long) z_first,
                     (unsigned long long) (z_first + zl_local - 1), (unsigned long long) zl_global);
     if (!(tau > 0.0)) return fail(LBM_B200_EINVAL, "tau must be positive (got %g)", tau);
-    if (yl + 2 > 65535 || zl_local + 2 > 65535) return fail(LBM_B200_EINVAL, "yl and zl are limited to 65533");
+    const uint64_t yl = axis == 1 ? zl_local : yl_all, zl = axis == 1 ? zl_all : zl_local;   // local lengths
+    if (yl + 2 > 65535 || zl + 2 > 65535) return fail(LBM_B200_EINVAL, "yl and zl are limited to 65533");
     const uint64_t P = (xl + 2 + 15) / 16 * 16;
-    const uint64_t plane = P * (yl + 2);
+    const uint64_t plane = P * ((axis == 1 ? zl : yl) + 2);         // one plane of the split axis
     const uint64_t qstride = plane * (zl_local + 2) + 16;
     if (qstride >= (1ull << 31)) return fail(LBM_B200_EINVAL, "slab too large: %llu padded cells per population (limit 2^31)", (unsigned long long) qstride);
 
@@ -876,8 +919,12 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
     lbm_b200* h = new lbm_b200();
     h->Q = Q;
     h->device = device;
-    h->g.xl = (int) xl; h->g.yl = (int) yl; h->g.zl = (int) zl_local;
+    h->axis = axis;
+    h->g.xl = (int) xl; h->g.yl = (int) yl; h->g.zl = (int) zl;
     h->g.P = (int) P; h->g.plane = (int) plane; h->g.qstride = (long long) qstride;
+    h->g.swap = axis == 1 ? 1 : 0;
+    h->g.sy = axis == 1 ? (int) plane : (int) P;
+    h->g.sz = axis == 1 ? (int) P : (int) plane;
     h->zl_global = (int) zl_global;
     h->z_first = (int) z_first;
     h->tau = tau;
@@ -888,7 +935,7 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
         double vel[27 * 3];
         lbm_b200_model(Q, vel, nullptr);
         for (int q = 0; q < Q; ++q)
-            h->pull_offset[q] = (long long) vel[3 * q + 2] * h->g.plane + (long long) vel[3 * q + 1] * h->g.P + (long long) vel[3 * q];
+            h->pull_offset[q] = (long long) vel[3 * q + 2] * h->g.sz + (long long) vel[3 * q + 1] * h->g.sy + (long long) vel[3 * q];
     }
     *out = h;   // so that the caller can destroy on failure below
     DeviceGuard guard(device);
@@ -923,6 +970,7 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
         h->sm_count = 148;
     }
     make_tensor_maps(h);
+    if (preload_step_kernels(Q) != 0) return bail(LBM_B200_ECUDA);
     CUB(cudaMalloc(&h->d_halo_error, sizeof(int)));
     CUB(cudaMemset(h->d_halo_error, 0, sizeof(int)));
     CUB(cudaHostAlloc(&h->h_halo_error, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
@@ -938,7 +986,7 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl, uint64_t zl
     CUB(cudaMemsetAsync(h->layer[0].bcid, 0, h->map_elems() * sizeof(uint16_t), h->stream));
 #undef CUB
     {
-        const uint64_t whole[6] = { 0, xl + 1, 0, yl + 1, 0, zl_global + 1 };
+        const uint64_t whole[6] = { 0, xl + 1, 0, yl_all + 1, 0, zl_all + 1 };
         LayerSel sel{ { &h->layer[0], nullptr }, 1 };
         if (paint_box(h, sel, whole, K_FLUID, 0) != 0) return bail(LBM_B200_ECUDA);
     }
@@ -990,12 +1038,17 @@ int lbm_b200_model_velocity_index(int Q, int u, int v, int w)
 
 int lbm_b200_create(lbm_b200_t** h, int Q, uint64_t xl, uint64_t yl, uint64_t zl, double tau, int device)
 {
-    return create_common(h, Q, xl, yl, zl, 1, zl, tau, device);
+    return create_common(h, Q, xl, yl, zl, 2, 1, zl, tau, device);
 }
 int lbm_b200_create_slab(lbm_b200_t** h, int Q, uint64_t xl, uint64_t yl, uint64_t zl_global, uint64_t z_first,
                          uint64_t zl_local, double tau, int device)
 {
-    return create_common(h, Q, xl, yl, zl_global, z_first, zl_local, tau, device);
+    return create_common(h, Q, xl, yl, zl_global, 2, z_first, zl_local, tau, device);
+}
+int lbm_b200_create_slab_axis(lbm_b200_t** h, int Q, uint64_t xl, uint64_t yl, uint64_t zl, int axis, uint64_t first,
+                              uint64_t local, double tau, int device)
+{
+    return create_common(h, Q, xl, yl, zl, axis, first, local, tau, device);
 }
 
 int lbm_b200_destroy(lbm_b200_t* h)
@@ -1212,7 +1265,7 @@ static int apply_fluid_mask(lbm_b200* h, const uint8_t* mask, int mask_z_first, 
     // the replicas of the neighbours' edge planes
     const int zoff = h->z_first - 1;                       // local z = global z - zoff
     const int lo = std::max(std::max(mask_z_first - zoff, 1 - zoff), 0);
-    const int hi = std::min(std::min(mask_z_first + mask_nz - 1 - zoff, h->zl_global - zoff), g.zl + 1);
+    const int hi = std::min(std::min(mask_z_first + mask_nz - 1 - zoff, h->zl_global - zoff), h->nslow() + 1);
     if (lo > hi) return 0;
     TRY(before_geometry_change(h));
     LayerSel sel;
@@ -1225,16 +1278,29 @@ static int apply_fluid_mask(lbm_b200* h, const uint8_t* mask, int mask_z_first, 
         h->h_bc.push_back(solid);
         TRY(sync_table(h));
     }
-    const size_t plane_cells = (size_t) g.xl * g.yl;
-    const int nz = hi - lo + 1;
-    const int first_mask_plane = lo + zoff - mask_z_first;     // index into `mask`
     DevBuf buf;
-    CU(cudaMalloc(&buf.p, plane_cells * nz));
-    CU(cudaMemcpyAsync(buf.p, mask + plane_cells * first_mask_plane, plane_cells * nz, cudaMemcpyHostToDevice, h->stream));
-    dim3 grid((g.xl + 127) / 128, g.yl, nz);
+    dim3 grid;
+    int y_lo, z_lo, mask_rows, y_shift, z_shift;
+    if (h->axis == 2) {
+        // mask planes are x-y planes: ship the planes [lo, hi] only
+        const size_t plane_cells = (size_t) g.xl * g.yl;
+        const int nz = hi - lo + 1;
+        const int first_mask_plane = lo + zoff - mask_z_first;     // index into `mask`
+        CU(cudaMalloc(&buf.p, plane_cells * nz));
+        CU(cudaMemcpyAsync(buf.p, mask + plane_cells * first_mask_plane, plane_cells * nz, cudaMemcpyHostToDevice, h->stream));
+        grid = dim3((g.xl + 127) / 128, g.yl, nz);
+        y_lo = 1; z_lo = lo; mask_rows = g.yl; y_shift = 1; z_shift = lo;
+    } else {
+        // y-slab: the rows [lo, hi] of every x-y plane of the mask (mask_nz rows per plane); the mask is bytes, ship it whole
+        const size_t bytes = (size_t) g.xl * mask_nz * g.zl;
+        CU(cudaMalloc(&buf.p, bytes));
+        CU(cudaMemcpyAsync(buf.p, mask, bytes, cudaMemcpyHostToDevice, h->stream));
+        grid = dim3((g.xl + 127) / 128, hi - lo + 1, g.zl);
+        y_lo = lo; z_lo = 1; mask_rows = mask_nz; y_shift = mask_z_first - zoff; z_shift = 1;
+    }
     for (int l = 0; l < sel.n; ++l) {
-        paint_mask_kernel<<<grid, 128, 0, h->stream>>>(buf.as<uint8_t>(), sel.l[l]->kind, sel.l[l]->bcid, g, lo, lo,
-                                                       (uint8_t) h->h_bc[id].kind, (uint16_t) id);
+        paint_mask_kernel<<<grid, 128, 0, h->stream>>>(buf.as<uint8_t>(), sel.l[l]->kind, sel.l[l]->bcid, g, y_lo, z_lo, mask_rows,
+                                                       y_shift, z_shift, (uint8_t) h->h_bc[id].kind, (uint16_t) id);
         h->launches++;
     }
     CU(cudaGetLastError());
@@ -1246,12 +1312,12 @@ static int apply_fluid_mask(lbm_b200* h, const uint8_t* mask, int mask_z_first, 
 int lbm_b200_set_fluid_mask(lbm_b200_t* h, const uint8_t* mask)
 {
     GUARD(h);
-    return apply_fluid_mask(h, mask, h->z_first, h->g.zl, 0, -1);
+    return apply_fluid_mask(h, mask, h->z_first, h->nslow(), 0, -1);
 }
 int lbm_b200_set_fluid_mask_literal(lbm_b200_t* h, const uint8_t* mask)
 {
     GUARD(h);
-    return apply_fluid_mask(h, mask, h->z_first, h->g.zl, 1, -1);
+    return apply_fluid_mask(h, mask, h->z_first, h->nslow(), 1, -1);
 }
 int lbm_b200_set_fluid_mask_global(lbm_b200_t* h, const uint8_t* mask, int literal)
 {
@@ -1306,6 +1372,7 @@ static int transfer_populations(lbm_b200* h, double* host, int layout, int field
     if (z_begin < 0 || z_count < 0 || z_begin + z_count > g.zl + 2) return fail(LBM_B200_EINVAL, "plane range outside the slab");
     if (layout == LBM_B200_SOA) {
         if (z_begin != 0 || z_count != g.zl + 2) return fail(LBM_B200_EINVAL, "plane ranges use the AoS layout");
+        if (g.swap) return fail(LBM_B200_EINVAL, "y-slabs transfer populations in the AoS layout only");
         const size_t n = h->ncell();
         for (int q = 0; q < Q; ++q) {
             double* d = dev + (size_t) q * g.qstride + X_SHIFT;
@@ -1473,7 +1540,7 @@ int lbm_b200_save_checkpoint(lbm_b200_t* h, const char* path)
     const Layout& g = h->g;
     CheckpointHeader hd{};
     memcpy(hd.magic, "LBMB200", 8);
-    hd.version = 2; hd.Q = h->Q;
+    hd.version = 2 + (h->axis == 1 ? 0x100 : 0); hd.Q = h->Q;       // y-slabs store x-z planes: another file layout
     hd.xl = g.xl; hd.yl = g.yl; hd.zl_local = g.zl; hd.z_first = h->z_first; hd.zl_global = h->zl_global;
     hd.arithmetic = h->exact ? LBM_B200_EXACT : LBM_B200_FAST;
     hd.steps = h->steps; hd.tau = h->tau;
@@ -1509,8 +1576,10 @@ int lbm_b200_load_checkpoint(lbm_b200_t* h, const char* path)
     CheckpointHeader hd{};
     int rc = 0;
     uint64_t my_hash = 0;
-    if (fread(&hd, sizeof hd, 1, fp) != 1 || memcmp(hd.magic, "LBMB200", 8) != 0 || hd.version != 2)
+    if (fread(&hd, sizeof hd, 1, fp) != 1 || memcmp(hd.magic, "LBMB200", 8) != 0 || (hd.version & 0xff) != 2)
         rc = fail(LBM_B200_EINVAL, "%s is not a lbm_b200 checkpoint (version 2)", path);
+    else if (hd.version != 2 + (h->axis == 1 ? 0x100 : 0))
+        rc = fail(LBM_B200_EINVAL, "%s was written by a slab with another split axis", path);
     else if (hd.Q != h->Q || hd.xl != g.xl || hd.yl != g.yl || hd.zl_local != g.zl || hd.z_first != h->z_first || hd.zl_global != h->zl_global)
         rc = fail(LBM_B200_EINVAL, "%s holds D3Q%d %dx%dx%d (slab at %d of %d), this domain is D3Q%d %dx%dx%d (slab at %d of %d)", path,
                   hd.Q, hd.xl, hd.yl, hd.zl_local, hd.z_first, hd.zl_global, h->Q, g.xl, g.yl, g.zl, h->z_first, h->zl_global);
@@ -1819,13 +1888,13 @@ int lbm_b200_halo_plane(lbm_b200_t* h, int buffer, int side, int k, int recv, vo
         using L = Lattice<decltype(Qc)::value>;
         int c = 0;
         for (int q = 0; q < h->Q; ++q)
-            if (L::cz(q) == want) { if (c == k) q_found = q; ++c; }
+            if ((h->axis == 1 ? L::cy(q) : L::cz(q)) == want) { if (c == k) q_found = q; ++c; }
         return 0;
     });
     if (q_found < 0) return fail(LBM_B200_EINVAL, "halo population index %d out of range", k);
     const Layout& g = h->g;
     int z;
-    if (side == LBM_B200_UP) z = recv ? g.zl + 1 : g.zl;
+    if (side == LBM_B200_UP) z = recv ? h->nslow() + 1 : h->nslow();
     else z = recv ? 0 : 1;
     // the cells of plane z occupy [z*plane + X_SHIFT, (z+1)*plane + X_SHIFT): rows are shifted by X_SHIFT elements
     *ptr = h->f[buffer] + (size_t) q_found * g.qstride + (size_t) z * g.plane + X_SHIFT;
@@ -1839,7 +1908,7 @@ int lbm_b200_edge_plane(lbm_b200_t* h, int side, int q, int recv, void** ptr)
     if (!h || !ptr) return fail(LBM_B200_EINVAL, "null argument");
     if (side < 0 || side > 1 || q < 0 || q >= h->Q) return fail(LBM_B200_EINVAL, "bad side / population");
     const Layout& g = h->g;
-    const int z = side == LBM_B200_UP ? (recv ? g.zl + 1 : g.zl) : (recv ? 0 : 1);
+    const int z = side == LBM_B200_UP ? (recv ? h->nslow() + 1 : h->nslow()) : (recv ? 0 : 1);
     *ptr = h->f[h->cur] + (size_t) q * g.qstride + (size_t) z * g.plane + X_SHIFT;
     return 0;
 }
@@ -1849,7 +1918,7 @@ int lbm_b200_step_edges(lbm_b200_t* h)
     GUARD(h);
     if (h->edges_done) return fail(LBM_B200_ESTATE, "step_edges called twice");
     TRY(ready_to_step(h));
-    if (h->g.zl > 1) TRY(launch_sweep(h, 1, 2, true, h->g.zl - 1, interior_mode(h)));
+    if (h->nslow() > 1) TRY(launch_sweep(h, 1, 2, true, h->nslow() - 1, interior_mode(h)));
     else TRY(launch_sweep(h, 1, 1, true, 1, interior_mode(h)));
     h->edges_done = true;
     return 0;
@@ -1858,7 +1927,7 @@ int lbm_b200_step_interior(lbm_b200_t* h)
 {
     GUARD(h);
     if (!h->edges_done) return fail(LBM_B200_ESTATE, "step_interior before step_edges");
-    TRY(sweep_planes(h, 2, h->g.zl - 2, true));
+    TRY(sweep_planes(h, 2, h->nslow() - 2, true));
     TRY(launch_inplace(h));
     return 0;
 }
@@ -1883,7 +1952,7 @@ int lbm_b200_halo_push_all(lbm_b200_t* h)
     for (int side = 0; side < 2; ++side) {
         double* peer = h->peer_f[side][h->cur];
         if (!peer) continue;
-        const int z_mine = side == LBM_B200_UP ? g.zl : 1;
+        const int z_mine = side == LBM_B200_UP ? h->nslow() : 1;
         for (int q = 0; q < h->Q; ++q)
             CU(cudaMemcpyAsync(peer + (size_t) q * h->peer_qstride[side] + h->peer_off[side],
                                h->f[h->cur] + (size_t) q * g.qstride + (size_t) z_mine * g.plane, bytes,
@@ -1896,7 +1965,7 @@ int lbm_b200_halo_pushed(lbm_b200_t* h)
 {
     if (!h) return fail(LBM_B200_EINVAL, "null handle");
     h->full_halo_at = h->steps;
-    h->materialized = false;
+    if (!h->first) h->materialized = false;     // (while `first` is set the boundary cells hold host-visible values: nothing to redo)
     return 0;
 }
 
@@ -1910,7 +1979,7 @@ int lbm_b200_export(lbm_b200_t* h, void* blob)
     CU(cudaIpcGetMemHandle(&mh, h->f[0]));
     static_assert(sizeof(mh) == 64, "CUDA IPC handle size");
     memcpy(p, &mh, 64);
-    long long meta[4] = { h->g.qstride, h->g.plane, h->g.zl, h->Q };
+    long long meta[4] = { h->g.qstride, h->g.plane, h->nslow() + 1000000LL * h->axis, h->Q };
     memcpy(p + 64, meta, sizeof meta);
     return 0;
 }
@@ -1918,7 +1987,10 @@ int lbm_b200_export(lbm_b200_t* h, void* blob)
 static int connect_common(lbm_b200* h, int side, double* base, unsigned long long* nb_flags, long long qstride,
                           long long plane, long long zl, long long Q)
 {
-    if (Q != h->Q || plane != h->g.plane) return fail(LBM_B200_EINVAL, "neighbour slab has a different lattice or x-y shape");
+    const long long nb_axis = zl / 1000000LL;      // (the split axis travels in the upper digits of the plane count)
+    zl %= 1000000LL;
+    if (Q != h->Q || plane != h->g.plane || nb_axis != h->axis)
+        return fail(LBM_B200_EINVAL, "neighbour slab has a different lattice, plane shape or split axis");
     // we are the neighbour's DOWN side when it is our UP side, and vice versa
     h->peer_flag[side] = nb_flags + (side == LBM_B200_UP ? LBM_B200_DOWN : LBM_B200_UP);
     h->peer_f[side][0] = base;
@@ -1985,7 +2057,7 @@ int lbm_b200_connect_local(lbm_b200_t* h, int side, lbm_b200_t* nb)
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(LBM_B200_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
         cudaGetLastError();
     }
-    return connect_common(h, side, nb->f[0], nb->d_flags, nb->g.qstride, nb->g.plane, nb->g.zl, nb->Q);
+    return connect_common(h, side, nb->f[0], nb->d_flags, nb->g.qstride, nb->g.plane, nb->nslow() + 1000000LL * nb->axis, nb->Q);
 }
 
 } // extern "C"

@@ -44,16 +44,21 @@ struct BcRec {          // one boundary handler object, device copy
 };
 
 struct Layout {
-    int xl, yl, zl;     // local interior lengths (zl = planes owned by this slab)
+    int xl, yl, zl;     // local interior lengths (of a slab: the planes it owns along the split axis)
     int P;              // row pitch (elements)
-    int plane;          // P * (yl+2)
+    int plane;          // elements of one plane of the SLOW (= split) axis: P * (other axis + 2)
+    int sy, sz;         // element strides of y and z: (P, plane) for z-slabs -- z slowest, like domain.hpp:61-64 --
+                        // and (plane, P) for y-slabs, whose x-z planes are the contiguous ones
+    int swap;           // 1: y is the slow axis
     long long qstride;  // elements between consecutive q arrays
 };
 
 LBM_HD inline int cell_at(const Layout& g, int x, int y, int z)
 {
-    return z * g.plane + y * g.P + x + X_SHIFT;
+    return z * g.sz + y * g.sy + x + X_SHIFT;
 }
+LBM_HD inline int n_slow(const Layout& g) { return g.swap ? g.yl : g.zl; }
+LBM_HD inline int n_mid(const Layout& g) { return g.swap ? g.zl : g.yl; }
 
 struct SweepParams {
     const double* __restrict__ src;   // collide field of the previous step
@@ -64,11 +69,11 @@ struct SweepParams {
     const uint16_t* __restrict__ bcid;
     const BcRec* __restrict__ bc;
     Layout g;
-    int z0;            // first plane swept by this launch
+    int z0;            // first plane (of the slow axis) swept by this launch
     int z_step;        // plane stride between consecutive blockIdx.z (1, or zl-1 for the two edge planes)
     int bx_shift;      // log2(threads along x per block)
     int first;         // 1: boundary cells still hold host-visible values -> pull stored
-    int wrap_z;        // periodic z is closed inside this slab
+    int wrap_z;        // the periodic slow axis is closed inside this slab
     double tau;
     double omega;      // 1/tau (fast mode)
     // per-population base pointers with the pull offset folded in, so that a bulk
@@ -77,8 +82,8 @@ struct SweepParams {
     const double* srcq[27];
     double* dstq[27];
     // optional remote copies of the slab-edge populations (peer ghost planes)
-    double* up_dst;    // receives c_z=+1 populations of plane z = zl
-    double* dn_dst;    // receives c_z=-1 populations of plane z = 1
+    double* up_dst;    // receives the c_slow=+1 populations of the last plane of the slow axis
+    double* dn_dst;    // receives the c_slow=-1 populations of its first plane
     long long up_qstride, dn_qstride;
     long long up_off, dn_off;   // element offset of the target ghost plane
 };
@@ -251,8 +256,8 @@ __device__ __noinline__ double freeslip_value(const double* __restrict__ src, co
 {
     const Tables<Q>& T = tables<Q>();
     const int dx = T.c[q][0], dy = T.c[q][1], dz = T.c[q][2];
-    const int b = iX - (dz * g.plane + dy * g.P + dx);
-    auto at = [&](int ox, int oy, int oz) { return b + oz * g.plane + oy * g.P + ox; };
+    const int b = iX - (dz * g.sz + dy * g.sy + dx);
+    auto at = [&](int ox, int oy, int oz) { return b + oz * g.sz + oy * g.sy + ox; };
     auto pick = [&](int cell, int u, int v, int w) {
         const int qq = T.q_of_cube[(w + 1) * 9 + (v + 1) * 3 + (u + 1)];
         return src[qq * g.qstride + cell];
@@ -308,7 +313,7 @@ __device__ __forceinline__ double link_value(const double* __restrict__ src, con
     case K_FREESLIP:
         return freeslip_value<Q>(src, kind, g, iX, q);
     default: {                                                // NULL / PARALLEL: stored value
-        return src[q * g.qstride + iX - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q))];
+        return src[q * g.qstride + iX - (L::cz(q) * g.sz + L::cy(q) * g.sy + L::cx(q))];
     }
     }
 }
@@ -363,11 +368,13 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
         static_for<Q>([&](auto I) {
             constexpr int q = decltype(I)::value;
             if (m & (1u << q)) {
-                const int s = i - (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
+                const int s = i - (L::cz(q) * g.sz + L::cy(q) * g.sy + L::cx(q));
                 const int k = p.kind[s];
                 if (k == K_PERIODIC) {
-                    const int sx = wrap1(x - L::cx(q), g.xl), sy = wrap1(y - L::cy(q), g.yl);
-                    const int sz = p.wrap_z ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
+                    // x and the middle axis always wrap inside the slab, the slow axis only if it is closed here
+                    const int sx = wrap1(x - L::cx(q), g.xl);
+                    const int sy = (!g.swap || p.wrap_z) ? wrap1(y - L::cy(q), g.yl) : y - L::cy(q);
+                    const int sz = (g.swap || p.wrap_z) ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
                     f[q] = p.src[q * g.qstride + cell_at(g, sx, sy, sz)];
                 } else if (!p.first) {   // first step: the stored value already pulled is the answer
                     f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, p.bc + p.bcid[s], om);
@@ -393,18 +400,19 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
         LBM_ST(p.dstq[q] + i, f[q]);
     });
     // slab edges: hand the populations that leave the slab to the neighbour (peer memory over NVLink)
-    if (p.up_dst != nullptr && z == g.zl) {
-        const int ip = i - z * g.plane;
+    const int slow = g.swap ? y : z;
+    if (p.up_dst != nullptr && slow == n_slow(g)) {
+        const int ip = i - slow * g.plane;
         static_for<Q>([&](auto I) {
             constexpr int q = decltype(I)::value;
-            if constexpr (L::cz(q) == 1) p.up_dst[q * p.up_qstride + p.up_off + ip] = f[q];
+            if ((g.swap ? L::cy(q) : L::cz(q)) == 1) p.up_dst[q * p.up_qstride + p.up_off + ip] = f[q];
         });
     }
-    if (p.dn_dst != nullptr && z == 1) {
-        const int ip = i - z * g.plane;
+    if (p.dn_dst != nullptr && slow == 1) {
+        const int ip = i - slow * g.plane;
         static_for<Q>([&](auto I) {
             constexpr int q = decltype(I)::value;
-            if constexpr (L::cz(q) == -1) p.dn_dst[q * p.dn_qstride + p.dn_off + ip] = f[q];
+            if ((g.swap ? L::cy(q) : L::cz(q)) == -1) p.dn_dst[q * p.dn_qstride + p.dn_off + ip] = f[q];
         });
     }
 }
@@ -425,10 +433,11 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
     const Layout& g = p.g;
     const int bx = 1 << p.bx_shift;
     const int x = 1 + blockIdx.x * bx + (threadIdx.x & (bx - 1));
-    const int y = 1 + blockIdx.y * (LBM_SWEEP_THREADS >> p.bx_shift) + (threadIdx.x >> p.bx_shift);
-    const int z = p.z0 + blockIdx.z * p.z_step;
-    if (x > g.xl || y > g.yl) return;
-    const int i = cell_at(g, x, y, z);
+    const int mid = 1 + blockIdx.y * (LBM_SWEEP_THREADS >> p.bx_shift) + (threadIdx.x >> p.bx_shift);
+    const int slow = p.z0 + blockIdx.z * p.z_step;          // planes of the slow axis: z, or y for y-slabs
+    if (x > g.xl || mid > n_mid(g)) return;
+    const int y = g.swap ? slow : mid, z = g.swap ? mid : slow;
+    const int i = slow * g.plane + mid * g.P + x + X_SHIFT;
     // Bulk cells read 1/8 byte of map, not 4.
     const uint32_t word = p.bits[i >> 5];
     uint32_t m = 0;
@@ -700,7 +709,8 @@ __global__ void materialize_kernel(double* __restrict__ field, const uint8_t* __
     const int y = blockIdx.y;
     const int z = blockIdx.z;
     if (x > g.xl + 1) return;
-    const bool in_interface = (z == 0 && lo_interface) || (z == g.zl + 1 && hi_interface);
+    const int slow = g.swap ? y : z, ns = n_slow(g), nm = n_mid(g);
+    const bool in_interface = (slow == 0 && lo_interface) || (slow == ns + 1 && hi_interface);
     const int b = cell_at(g, x, y, z);
     const int k = kind[b];
     if (k < K_NOSLIP || k > K_PRESSURE) return;
@@ -708,11 +718,12 @@ __global__ void materialize_kernel(double* __restrict__ field, const uint8_t* __
     static_for<Q>([&](auto I) {
         constexpr int q = decltype(I)::value;
         const int nx = x + L::cx(q), ny = y + L::cy(q), nz = z + L::cz(q);
-        bool inb = nx > 0 && nx < g.xl + 1 && ny > 0 && ny < g.yl + 1;
-        if (in_interface) inb = inb && nz > 0 && nz < g.zl + 1;
-        else inb = inb && (nz > 0 || (nz == 0 && z_lo_open)) && (nz < g.zl + 1 || (nz == g.zl + 1 && z_hi_open));
+        const int n_s = g.swap ? ny : nz, n_m = g.swap ? nz : ny;       // neighbour along the slow / middle axis
+        bool inb = nx > 0 && nx < g.xl + 1 && n_m > 0 && n_m < nm + 1;
+        if (in_interface) inb = inb && n_s > 0 && n_s < ns + 1;
+        else inb = inb && (n_s > 0 || (n_s == 0 && z_lo_open)) && (n_s < ns + 1 || (n_s == ns + 1 && z_hi_open));
         if (inb) {
-            const int n = b + (L::cz(q) * g.plane + L::cy(q) * g.P + L::cx(q));
+            const int n = b + (L::cz(q) * g.sz + L::cy(q) * g.sy + L::cx(q));
             if (kind[n] == K_FLUID) {
                 OwnMoments om;
                 om.have = false;
@@ -809,7 +820,7 @@ __global__ void fill_weights_kernel(double* __restrict__ field, long long qstrid
 //   MASK_NOCOLLIDE  X is streamed but not BGK-collided
 // counters[0] += cells that are collided in place without being streamed (fluid in the destination lattice,
 // but in the ghost shell or not fluid in the source lattice; domain.hpp:147-155 loops 0..l+1);
-// counters[1] |= 1 if a z ghost plane of the physical shell carries PERIODIC;
+// counters[1] |= 1 if a ghost plane of the slow axis that belongs to the physical shell carries PERIODIC;
 // counters[3] += interior cells that are not streamed (solid in the source lattice).
 template <int Q>
 __global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const uint8_t* __restrict__ kind_dst,
@@ -829,7 +840,7 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const ui
         m = MASK_SKIP;
     } else {
         for (int q = 0; q < Q; ++q) {
-            const int s = i - (T.c[q][2] * g.plane + T.c[q][1] * g.P + T.c[q][0]);
+            const int s = i - (T.c[q][2] * g.sz + T.c[q][1] * g.sy + T.c[q][0]);
             if (kind_src[s] != K_FLUID) m |= 1u << q;
         }
         if (kind_dst[i] != K_FLUID) m |= MASK_NOCOLLIDE;
@@ -837,10 +848,11 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const ui
     mask[i] = m;
     if (m) atomicOr(&bits[i >> 5], 1u << (i & 31));   // bits zeroed by the caller
     if ((m & MASK_SKIP) && interior) atomicAdd(&counters[3], 1u);
-    const bool neighbours_cell = (z == 0 && lo_interface) || (z == g.zl + 1 && hi_interface);
+    const int slow = g.swap ? y : z;
+    const bool neighbours_cell = (slow == 0 && lo_interface) || (slow == n_slow(g) + 1 && hi_interface);
     if (!neighbours_cell) {
         if (!streamed && kind_dst[i] == K_FLUID) atomicAdd(&counters[0], 1u);
-        if ((z == 0 || z == g.zl + 1) && kind_src[i] == K_PERIODIC) atomicOr(&counters[1], 1u);
+        if ((slow == 0 || slow == n_slow(g) + 1) && kind_src[i] == K_PERIODIC) atomicOr(&counters[1], 1u);
     }
 }
 
@@ -853,7 +865,8 @@ __global__ void collect_inplace_kernel(const uint8_t* __restrict__ kind_src, con
     const int y = blockIdx.y;
     const int z = blockIdx.z;
     if (x > g.xl + 1) return;
-    if ((z == 0 && lo_interface) || (z == g.zl + 1 && hi_interface)) return;
+    const int slow = g.swap ? y : z;
+    if ((slow == 0 && lo_interface) || (slow == n_slow(g) + 1 && hi_interface)) return;
     const int i = cell_at(g, x, y, z);
     const bool interior = x > 0 && x < g.xl + 1 && y > 0 && y < g.yl + 1 && z > 0 && z < g.zl + 1;
     const bool streamed = interior && kind_src[i] == K_FLUID;
@@ -874,16 +887,17 @@ __global__ void paint_box_kernel(uint8_t* __restrict__ kind, uint16_t* __restric
     bcid[i] = id;
 }
 
-// the loop of io/vtk.hpp:141-150: mask value 0 => the solid handler.  `mask` holds x-y planes of interior
-// cells; local plane z of this slab takes mask plane (z - mask_z_shift).
+// the loop of io/vtk.hpp:141-150: mask value 0 => the solid handler.  `mask` holds x-y planes of interior cells,
+// `mask_rows` rows each; local cell (x, y, z) takes mask element (x-1, y - y_shift, z - z_shift).  Painted: local
+// rows [y_lo, y_lo + gridDim.y) of local planes [z_lo, z_lo + gridDim.z).
 __global__ void paint_mask_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ kind, uint16_t* __restrict__ bcid,
-                                  const Layout g, int z_lo, int mask_z_shift, uint8_t k, uint16_t id)
+                                  const Layout g, int y_lo, int z_lo, int mask_rows, int y_shift, int z_shift, uint8_t k, uint16_t id)
 {
     const int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = 1 + blockIdx.y;
+    const int y = y_lo + blockIdx.y;
     const int z = z_lo + blockIdx.z;
     if (x > g.xl) return;
-    const size_t o = ((size_t) (z - mask_z_shift) * g.yl + (y - 1)) * g.xl + (x - 1);
+    const size_t o = ((size_t) (z - z_shift) * mask_rows + (y - y_shift)) * g.xl + (x - 1);
     if (!mask[o]) {
         const int i = cell_at(g, x, y, z);
         kind[i] = k;
@@ -895,7 +909,7 @@ __global__ void paint_mask_kernel(const uint8_t* __restrict__ mask, uint8_t* __r
 // in-bounds fluid neighbour (the q loop includes the rest velocity, so fluid cells never qualify) take the
 // do-nothing handler.  Tagging never changes who is fluid, so it can be done in place.
 template <int Q>
-__global__ void tag_null_kernel(uint8_t* __restrict__ kind, const Layout g, int z_first, int zl_global,
+__global__ void tag_null_kernel(uint8_t* __restrict__ kind, const Layout g, int slow_first, int slow_global,
                                 unsigned int* __restrict__ count)
 {
     const Tables<Q>& T = tables<Q>();
@@ -907,9 +921,10 @@ __global__ void tag_null_kernel(uint8_t* __restrict__ kind, const Layout g, int 
     if (kind[i] == K_FLUID) return;
     for (int q = 0; q < Q; ++q) {
         const int nx = x + T.c[q][0], ny = y + T.c[q][1], nz = z + T.c[q][2];
-        const int gz = nz + z_first - 1;
-        if (nx > 0 && nx < g.xl + 1 && ny > 0 && ny < g.yl + 1 && gz > 0 && gz < zl_global + 1
-            && kind[i + (T.c[q][2] * g.plane + T.c[q][1] * g.P + T.c[q][0])] == K_FLUID)
+        const int n_m = g.swap ? nz : ny;                                  // middle axis: local == global
+        const int gs = (g.swap ? ny : nz) + slow_first - 1;               // slow axis: global index of the neighbour
+        if (nx > 0 && nx < g.xl + 1 && n_m > 0 && n_m < n_mid(g) + 1 && gs > 0 && gs < slow_global + 1
+            && kind[i + (T.c[q][2] * g.sz + T.c[q][1] * g.sy + T.c[q][0])] == K_FLUID)
             return;
     }
     if (kind[i] != K_NULL) atomicAdd(count, 1u);

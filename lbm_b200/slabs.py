@@ -209,19 +209,20 @@ class SlabRunner:
 
 
 class LocalSlabStack:
-    """N z-slabs driven from ONE process (what the C++ Domain does for `gpus = N`): slabs may sit on
+    """N slabs driven from ONE process (what the C++ Domain does for `gpus = N`): slabs may sit on
     different GPUs (peer access over NVLink) or, for testing the exchange logic on a single GPU, on
-    the same device."""
+    the same device.  axis = capi.AXIS_Z splits into z-slabs (x-y planes), capi.AXIS_Y into y-slabs
+    (x-z planes) -- for domains whose z extent is shorter than the number of slabs, or flat ones."""
 
     def __init__(self, Q, xl, yl, zl, tau, boxes, n_slabs, devices=None, exact=False, fluid_mask=None,
-                 periodic_z=False):
+                 periodic_z=False, axis=capi.AXIS_Z):
         import numpy as np
         self.np = np
-        self.Q, self.xl, self.yl, self.zl = Q, xl, yl, zl
-        self.periodic_z = periodic_z and n_slabs > 1
-        self.ranges = partition(zl, n_slabs)
+        self.Q, self.xl, self.yl, self.zl, self.axis = Q, xl, yl, zl, axis
+        self.periodic_z = periodic_z and n_slabs > 1      # periodic along the split axis: a ring of slabs
+        self.ranges = partition(yl if axis == capi.AXIS_Y else zl, n_slabs)
         devices = devices or [0] * n_slabs
-        self.slabs = [capi.Domain(Q, xl, yl, zl, tau, device=devices[r], z_first=zf, zl_local=nz, exact=exact)
+        self.slabs = [capi.Domain(Q, xl, yl, zl, tau, device=devices[r], z_first=zf, zl_local=nz, exact=exact, axis=axis)
                       for r, (zf, nz) in enumerate(self.ranges)]
         for (zf, nz), s in zip(self.ranges, self.slabs):
             if fluid_mask is not None:      # every slab also needs the rows of its neighbours' edge planes
@@ -235,17 +236,21 @@ class LocalSlabStack:
             if down is not None:
                 self.slabs[r].connect_local(DOWN, self.slabs[down])
 
+    def _cut(self, a, lo, hi):
+        """planes lo..hi-1 of the split axis of an array shaped [z, y, ...]"""
+        return a[:, lo:hi] if self.axis == capi.AXIS_Y else a[lo:hi]
+
     def upload(self, f):
         """f: [(xl+2)(yl+2)(zl+2), Q] global AoS; every slab gets its planes plus both ghost planes
         (for a periodic ring the two global ghost planes are first filled with their wrapped images)"""
         np = self.np
-        plane = (self.xl + 2) * (self.yl + 2)
-        f = np.array(f, dtype=np.float64).reshape(self.zl + 2, plane, self.Q)
+        f = np.array(f, dtype=np.float64).reshape(self.zl + 2, self.yl + 2, (self.xl + 2) * self.Q)
+        n = self.yl if self.axis == capi.AXIS_Y else self.zl
         if self.periodic_z:
-            f[0] = f[self.zl]
-            f[self.zl + 1] = f[1]
+            self._cut(f, 0, 1)[...] = self._cut(f, n, n + 1)
+            self._cut(f, n + 1, n + 2)[...] = self._cut(f, 1, 2)
         for (zf, nz), s in zip(self.ranges, self.slabs):
-            s.upload(np.ascontiguousarray(f[zf - 1:zf + nz + 1]))
+            s.upload(np.ascontiguousarray(self._cut(f, zf - 1, zf + nz + 1)))
 
     def step(self, n=1):
         capi.step_group(self.slabs, n)
@@ -266,14 +271,14 @@ class LocalSlabStack:
     def download(self):
         """global AoS populations; interface ghost planes are taken from their owners"""
         np = self.np
-        plane = (self.xl + 2) * (self.yl + 2)
-        out = np.empty((self.zl + 2, plane, self.Q))
+        row = (self.xl + 2) * self.Q
+        out = np.empty((self.zl + 2, self.yl + 2, row))
         self.prepare_readback()
         for i, ((zf, nz), s) in enumerate(zip(self.ranges, self.slabs)):
-            loc = s.download().reshape(nz + 2, plane, self.Q)
+            loc = s.download().reshape(s.zl + 2, s.yl + 2, row)
             lo = 0 if i == 0 else 1
             hi = nz + 2 if i == len(self.slabs) - 1 else nz + 1
-            out[zf - 1 + lo:zf - 1 + hi] = loc[lo:hi]
+            self._cut(out, zf - 1 + lo, zf - 1 + hi)[...] = self._cut(loc, lo, hi)
         return out.reshape(-1, self.Q)
 
     def macroscopic(self):
@@ -283,8 +288,8 @@ class LocalSlabStack:
         self.prepare_readback()
         for (zf, nz), s in zip(self.ranges, self.slabs):
             r, v = s.macroscopic()
-            rho[zf - 1:zf - 1 + nz] = r
-            u[zf - 1:zf - 1 + nz] = v
+            self._cut(rho, zf - 1, zf - 1 + nz)[...] = r
+            self._cut(u, zf - 1, zf - 1 + nz)[...] = v
         return rho, u
 
     def close(self):

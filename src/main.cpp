@@ -32,7 +32,7 @@ int simulate(lbm::io::Config& cfg)
     auto domain = lbm::io::parse_scenario_file<model>(cfg.scenario_xml(), cfg, collision);
     std::cout << cfg << std::endl;
     std::cout << "> Lattice:                " << model::name << '\n'
-              << "> GPUs (z-slabs):         " << domain->gpu_count() << '\n'
+              << "> GPUs (" << domain->split_axis_name() << "-slabs):         " << domain->gpu_count() << '\n'
               << "> Arithmetic:             " << cfg.arithmetic() << std::endl;
     std::cout << "> Domain lengths (x,y,z): " << domain->xlength() << ", " << domain->ylength() << ", "
               << domain->zlength() << std::endl;

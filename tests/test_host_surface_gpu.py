@@ -51,9 +51,12 @@ def read_dump(path, steps):
 
 @pytest.mark.parametrize("Q", [15, 19, 27])
 @pytest.mark.parametrize("name", sorted(SCENARIOS))
-@pytest.mark.parametrize("gpus", [1, 2])
+@pytest.mark.parametrize("gpus", [1, 2, "2y"])
 def test_reference_style_calls_match_oracle(exe, tmp_path, Q, name, gpus):
+    """gpus = "2y": the same two-GPU Domain split along y (x-z planes) instead of z"""
     from lbm_b200 import capi
+    axis = "y" if gpus == "2y" else "z"
+    gpus = int(str(gpus)[0])
     if gpus > capi.device_count():
         pytest.skip("needs %d GPUs" % gpus)
     xml, case = SCENARIOS[name]
@@ -61,7 +64,7 @@ def test_reference_style_calls_match_oracle(exe, tmp_path, Q, name, gpus):
     cfg = tmp_path / "run.cfg"
     cfg.write_text("tau = 0.6\ntimesteps = %d\ntimesteps-per-plot = 0\noutput-dir = %s\nscenario-file = %s\n"
                    % (steps, tmp_path / "vtk", os.path.join(ROOT, xml)))
-    env = dict(os.environ, LBM_B200_ARITHMETIC="exact", LBM_B200_GPUS=str(gpus))
+    env = dict(os.environ, LBM_B200_ARITHMETIC="exact", LBM_B200_GPUS=str(gpus), LBM_B200_SPLIT_AXIS=axis)
     dump = tmp_path / "dump.bin"
     r = subprocess.run([exe, str(Q), str(cfg), str(steps), str(dump)], cwd=ROOT, env=env, capture_output=True, text=True)
     assert r.returncode == 0 and "HOST_API_CHECK DONE gpus=%d" % gpus in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
