@@ -89,6 +89,17 @@ def test_reference_style_calls_match_oracle(exe, tmp_path, Q, name, gpus):
     assert re.search(rb'WholeExtent="0 %d 0 %d 0 %d"' % (case["xl"] - 1, case["yl"] - 1, case["zl"] - 1), blob)
 
 
+def test_create_subdomain_like_the_reference(tmp_path):
+    """Domain::create_subdomain (domain.hpp:197-248): extents, copied cells, handlers of the cut / outer faces"""
+    exe = str(tmp_path / "subdomain_check")
+    compile_cpp(os.path.join(ROOT, "tests", "cpp", "subdomain_check.cpp"), exe)
+    cfg = tmp_path / "c.cfg"
+    cfg.write_text("tau = 0.6\ntimesteps = 1\ntimesteps-per-plot = 0\noutput-dir = %s\nscenario-file = %s\n"
+                   % (tmp_path / "vtk", os.path.join(ROOT, "scenarios", "step_small.xml")))
+    r = subprocess.run([exe, str(cfg)], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and "SUBDOMAIN_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_command_line_driver_runs_a_scenario(tmp_path):
     exe = str(tmp_path / "lbm")
     compile_cpp(os.path.join(ROOT, "src", "main.cpp"), exe)
