@@ -30,6 +30,9 @@ enum : int {
 constexpr uint32_t MASK_SKIP = 0x80000000u;       // not streamed: not an interior cell, or not fluid in the source lattice
 constexpr uint32_t MASK_NOCOLLIDE = 0x40000000u;  // streamed, but the destination lattice's handler is not the fluid one
                                                   // (only when the two lattices carry different handlers, see GeoLayer)
+constexpr uint32_t MASK_ALLNOSLIP = 0x20000000u;  // every flagged pull source is a NoSlipBoundary cell: the wall path needs
+                                                  // no handler look-ups, only the cell's own inverse populations
+constexpr uint32_t MASK_ALLPERIODIC = 0x10000000u; // every flagged pull source is a PERIODIC ghost cell: wrapped pulls
 constexpr int X_SHIFT = 15;                   // element offset of x = 0 inside a row
 constexpr int TMA_X0 = X_SHIFT - 1;           // the tensor maps of the TMA-fed sweep view rows from this element on:
                                               // 16-byte aligned, x = 0 .. xl+1 at coordinates 1 .. xl+2 of ONE row of
@@ -362,7 +365,26 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
 {
     using L = Lattice<Q>;
     const Layout& g = p.g;
-    if (m != 0) {
+    if ((m & MASK_ALLNOSLIP) && !p.first) {
+        // the common wall cell (plain bounce-back, boundary.hpp:28): B[q] = f_inv(q)(X) of the previous step for every
+        // flagged direction -- independent loads of the cell's own populations, ONE round trip after the mask instead
+        // of kind -> handler -> value per direction
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            if (m & (1u << q)) f[q] = p.src[L::inv(q) * g.qstride + i];
+        });
+    } else if (m & MASK_ALLPERIODIC) {
+        // x and the middle axis always wrap inside the slab, the slow axis only if it is closed here
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            if (m & (1u << q)) {
+                const int sx = wrap1(x - L::cx(q), g.xl);
+                const int sy = (!g.swap || p.wrap_z) ? wrap1(y - L::cy(q), g.yl) : y - L::cy(q);
+                const int sz = (g.swap || p.wrap_z) ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
+                f[q] = p.src[q * g.qstride + cell_at(g, sx, sy, sz)];
+            }
+        });
+    } else if (m != 0) {
         OwnMoments om;
         om.have = false;
         static_for<Q>([&](auto I) {
@@ -381,10 +403,12 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
                 }
             }
         });
+    }
+    if constexpr (SPLIT) {
         // SPLIT (the two lattices carry different handlers, "literal" edits): a cell can be streamed into although
         // its handler in the destination lattice is a boundary -- stored as streamed, not collided.  A separate
         // instantiation: carrying this exit in the common kernel costs D3Q27 1.8 % (profiles/variants_r08_wall.txt)
-        if constexpr (SPLIT) if (m & MASK_NOCOLLIDE) {
+        if (m & MASK_NOCOLLIDE) {
             static_for<Q>([&](auto I) {
                 constexpr int q = decltype(I)::value;
                 p.dstq[q][i] = f[q];
@@ -839,10 +863,18 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const ui
     if (!streamed) {
         m = MASK_SKIP;
     } else {
+        bool only_noslip = true, only_periodic = true;
         for (int q = 0; q < Q; ++q) {
             const int s = i - (T.c[q][2] * g.sz + T.c[q][1] * g.sy + T.c[q][0]);
-            if (kind_src[s] != K_FLUID) m |= 1u << q;
+            const int k = kind_src[s];
+            if (k != K_FLUID) {
+                m |= 1u << q;
+                only_noslip = only_noslip && k == K_NOSLIP;
+                only_periodic = only_periodic && k == K_PERIODIC;
+            }
         }
+        if (m && only_noslip) m |= MASK_ALLNOSLIP;
+        if (m && only_periodic) m |= MASK_ALLPERIODIC;
         if (kind_dst[i] != K_FLUID) m |= MASK_NOCOLLIDE;
     }
     mask[i] = m;
