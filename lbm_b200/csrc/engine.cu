@@ -371,7 +371,7 @@ int build_step_maps(lbm_b200* h, int src, int dst, bool* periodic_z)
     CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned int), h->stream));
     const int lo = h->lo_interface(), hi = h->hi_interface();
     dispatch_q(h->Q, [&](auto Qc) {
-        build_mask_kernel<decltype(Qc)::value><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(S.kind, D.kind, S.mask, S.bits, g, lo, hi, h->d_counters);
+        build_mask_kernel<decltype(Qc)::value><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(S.kind, D.kind, S.bcid, S.mask, S.bits, g, lo, hi, h->d_counters);
         return 0;
     });
     h->launches++;

@@ -33,6 +33,8 @@ constexpr uint32_t MASK_NOCOLLIDE = 0x40000000u;  // streamed, but the destinati
 constexpr uint32_t MASK_ALLNOSLIP = 0x20000000u;  // every flagged pull source is a NoSlipBoundary cell: the wall path needs
                                                   // no handler look-ups, only the cell's own inverse populations
 constexpr uint32_t MASK_ALLPERIODIC = 0x10000000u; // every flagged pull source is a PERIODIC ghost cell: wrapped pulls
+constexpr uint32_t MASK_ONEHANDLER = 0x08000000u;  // every flagged pull source carries the SAME handler object (kind and id):
+                                                   // looked up once (an inflow / outflow / moving-wall face)
 constexpr int X_SHIFT = 15;                   // element offset of x = 0 inside a row
 constexpr int TMA_X0 = X_SHIFT - 1;           // the tensor maps of the TMA-fed sweep view rows from this element on:
                                               // 16-byte aligned, x = 0 .. xl+1 at coordinates 1 .. xl+2 of ONE row of
@@ -383,6 +385,19 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
                 const int sz = (g.swap || p.wrap_z) ? wrap1(z - L::cz(q), g.zl) : z - L::cz(q);
                 f[q] = p.src[q * g.qstride + cell_at(g, sx, sy, sz)];
             }
+        });
+    } else if ((m & MASK_ONEHANDLER) && !p.first) {
+        // one handler for all flagged directions: its kind and record are fetched once, through the first flagged source
+        const Tables<Q>& T = tables<Q>();
+        const int q0 = __ffs(m) - 1;
+        const int s0 = i - (T.c[q0][2] * g.sz + T.c[q0][1] * g.sy + T.c[q0][0]);
+        const int k = p.kind[s0];
+        const BcRec* rec = p.bc + p.bcid[s0];
+        OwnMoments om;
+        om.have = false;
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            if (m & (1u << q)) f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, rec, om);
         });
     } else if (m != 0) {
         OwnMoments om;
@@ -848,6 +863,7 @@ __global__ void fill_weights_kernel(double* __restrict__ field, long long qstrid
 // counters[3] += interior cells that are not streamed (solid in the source lattice).
 template <int Q>
 __global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const uint8_t* __restrict__ kind_dst,
+                                  const uint16_t* __restrict__ bcid_src,
                                   uint32_t* __restrict__ mask, uint32_t* __restrict__ bits, const Layout g,
                                   const int lo_interface, const int hi_interface, unsigned int* __restrict__ counters)
 {
@@ -863,7 +879,8 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const ui
     if (!streamed) {
         m = MASK_SKIP;
     } else {
-        bool only_noslip = true, only_periodic = true;
+        bool only_noslip = true, only_periodic = true, one_handler = true;
+        int k0 = -1, id0 = -1;
         for (int q = 0; q < Q; ++q) {
             const int s = i - (T.c[q][2] * g.sz + T.c[q][1] * g.sy + T.c[q][0]);
             const int k = kind_src[s];
@@ -871,8 +888,13 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const ui
                 m |= 1u << q;
                 only_noslip = only_noslip && k == K_NOSLIP;
                 only_periodic = only_periodic && k == K_PERIODIC;
+                const int id = bcid_src[s];
+                if (k0 < 0) { k0 = k; id0 = id; }
+                one_handler = one_handler && k == k0 && id == id0;
             }
         }
+        // (FreeSlip looks at the neighbours of each boundary cell, Null / Parallel / Periodic use stored values)
+        if (m && one_handler && (k0 == K_MOVINGWALL || k0 == K_INFLOW || k0 == K_OUTFLOW || k0 == K_PRESSURE)) m |= MASK_ONEHANDLER;
         if (m && only_noslip) m |= MASK_ALLNOSLIP;
         if (m && only_periodic) m |= MASK_ALLPERIODIC;
         if (kind_dst[i] != K_FLUID) m |= MASK_NOCOLLIDE;
