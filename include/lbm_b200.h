@@ -245,6 +245,11 @@ int lbm_b200_macroscopic_end(lbm_b200_t* h);
 /* page-locked host memory placed on the NUMA node next to `device` (device < 0: the current one) */
 int lbm_b200_host_alloc(void** ptr, size_t bytes, int device);
 int lbm_b200_host_free(void* ptr);
+/* Self-test of the bit-identical mode's division (kernels.cuh: div_rcp): the reference divides by C_S*C_S, 2*C_S^4,
+ * 2*C_S^2 (collision.hpp:47-48), tau (:68) and rho (:27-29); the device computes these quotients from a correctly
+ * rounded reciprocal with two FMA corrections.  Compares n operands per divisor with IEEE division on the device;
+ * *mismatches must come back 0. */
+int lbm_b200_selftest_division(uint64_t n, uint64_t seed, double tau, uint64_t* mismatches);
 /* pins the calling host thread to the CPUs next to `device` (no-op where the topology is unknown) */
 int lbm_b200_bind_host_thread(int device);
 /* reductions for physics checks: sum of density, sum of |u|^2, max |u| over

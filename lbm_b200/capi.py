@@ -36,7 +36,7 @@ SYMBOLS = [
     "lbm_b200_save_checkpoint", "lbm_b200_load_checkpoint", "lbm_b200_upload_planes", "lbm_b200_download_planes",
     "lbm_b200_step", "lbm_b200_step_group", "lbm_b200_set_graphs", "lbm_b200_set_sweep_engine", "lbm_b200_sync", "lbm_b200_elapsed_ms", "lbm_b200_launch_count", "lbm_b200_tma_launch_count", "lbm_b200_steps_done",
     "lbm_b200_macroscopic", "lbm_b200_macroscopic_begin", "lbm_b200_macroscopic_end", "lbm_b200_diagnostics",
-    "lbm_b200_host_alloc", "lbm_b200_host_free", "lbm_b200_bind_host_thread",
+    "lbm_b200_host_alloc", "lbm_b200_host_free", "lbm_b200_bind_host_thread", "lbm_b200_selftest_division",
     "lbm_b200_halo_layout", "lbm_b200_halo_plane", "lbm_b200_edge_plane", "lbm_b200_dst_buffer",
     "lbm_b200_step_edges", "lbm_b200_step_interior", "lbm_b200_step_finish",
     "lbm_b200_export", "lbm_b200_connect", "lbm_b200_connect_local", "lbm_b200_halo_push_all", "lbm_b200_halo_pushed",
@@ -93,6 +93,7 @@ lib.lbm_b200_macroscopic_end.argtypes = [_H]
 lib.lbm_b200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
 lib.lbm_b200_host_free.argtypes = [C.c_void_p]
 lib.lbm_b200_bind_host_thread.argtypes = [C.c_int]
+lib.lbm_b200_selftest_division.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.POINTER(C.c_uint64)]
 lib.lbm_b200_upload_populations.argtypes = [_H, C.c_void_p, C.c_int, C.c_int]
 lib.lbm_b200_download_populations.argtypes = [_H, C.c_void_p, C.c_int, C.c_int]
 lib.lbm_b200_init_equilibrium.argtypes = [_H, C.c_void_p, C.c_void_p]
@@ -129,6 +130,13 @@ def _check(rc):
 
 def device_count():
     return lib.lbm_b200_device_count()
+
+
+def selftest_division(n, seed=1, tau=0.6):
+    """mismatches between the bit-identical mode's reciprocal-based quotients and IEEE division on n operands per divisor"""
+    bad = C.c_uint64(0)
+    _check(lib.lbm_b200_selftest_division(n, seed, tau, C.byref(bad)))
+    return bad.value
 
 
 def model(Q):

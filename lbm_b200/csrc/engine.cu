@@ -93,6 +93,7 @@ struct GeoLayer {
     uint8_t* kind = nullptr;
     uint16_t* bcid = nullptr;
     uint32_t* mask = nullptr;      // link mask of the steps whose SOURCE is this buffer
+    int xhint_lo = 0, xhint_hi = 0;   // SweepParams::xhint_* of those steps
     uint32_t* bits = nullptr;
     int* inplace = nullptr;        // cells BGK-collided in place when this buffer is the DESTINATION
     int n_inplace = 0;
@@ -167,6 +168,7 @@ struct lbm_b200 {
     int* h_halo_error_dev = nullptr;                // its device address
     int clock_khz = 1965000;
     int sweep_mode = -1;                            // SWEEP_* for the interior launch; -1: chosen per geometry (LBM_B200_SWEEP_MODE)
+    int xface_mode = 1;                             // 1: SWEEP_XFACE where the host has a guess for an x face (LBM_B200_XFACE=0: never)
     // TMA-fed sweep (sweep_tma_kernel): 1 where possible, 0 / -1 never (LBM_B200_TMA) -- an opt-in engine
     int tma_mode = -1;
     int tma_bx = 0;                                 // box width chosen for this lattice (0: no tensor maps)
@@ -174,6 +176,7 @@ struct lbm_b200 {
     CUtensorMap tmap[2][2];                         // [buffer][shifted]: 4-D views (x, y, z, q) of the two lattices,
                                                     // box bx x 256/bx, and (bx+2) x 256/bx for populations with c_x != 0
     long long pull_offset[27] = {};                 // c_z*plane + c_y*P + c_x per direction
+    int cvel_x[27] = {};                            // c_x per direction
     unsigned long long* d_trace = nullptr;         // LBM_B200_HALO_TRACE=<file prefix>: wait-kernel timestamps
     static constexpr int TRACE_EPOCHS = 8192;
 
@@ -369,6 +372,7 @@ int build_step_maps(lbm_b200* h, int src, int dst, bool* periodic_z)
     CU(cudaMemsetAsync(S.mask, 0x80, h->map_elems() * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(S.bits, 0, h->bits_words() * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned int), h->stream));
+    CU(cudaMemsetAsync(h->d_counters + 8, 0, 4 * sizeof(unsigned int), h->stream));
     const int lo = h->lo_interface(), hi = h->hi_interface();
     dispatch_q(h->Q, [&](auto Qc) {
         build_mask_kernel<decltype(Qc)::value><<<map_grid(g, g.zl + 2), 128, 0, h->stream>>>(S.kind, D.kind, S.bcid, S.mask, S.bits, g, lo, hi, h->d_counters);
@@ -376,9 +380,21 @@ int build_step_maps(lbm_b200* h, int src, int dst, bool* periodic_z)
     });
     h->launches++;
     CU(cudaGetLastError());
-    unsigned int c[4];
+    unsigned int c[12];
     CU(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    // what the cells of the two x faces mostly see next to them (SweepParams::xhint_*; only a guess that the
+    // kernel checks against each cell's link mask)
+    const long long face_cells = (long long) std::max(g.yl - 2, 0) * std::max(g.zl - 2, 0);
+    for (int side = 0; side < 2; ++side) {
+        const unsigned int noslip = c[8 + 2 * side], periodic = c[9 + 2 * side];
+        int hint = 0;
+        if (g.xl >= 2 && face_cells > 0) {
+            if (2ll * noslip > face_cells) hint = 1;
+            else if (2ll * periodic > face_cells) hint = 2;
+        }
+        (side == 0 ? S.xhint_lo : S.xhint_hi) = hint;
+    }
     if (c[1] & 1u) *periodic_z = true;
     if (D.inplace) CU(cudaFree(D.inplace));
     D.inplace = nullptr;
@@ -445,6 +461,8 @@ void fill_sweep_params(lbm_b200* h, SweepParams& p, int z0, bool with_peers, int
     while (shift > 5 && (1 << (shift - 1)) >= g.xl) --shift;   // ... unless the row is short
     p.bx_shift = shift;
     p.first = h->first ? 1 : 0;
+    p.xhint_lo = h->first ? 0 : S.xhint_lo;     // (first step: wall values are the stored ones, nothing to guess)
+    p.xhint_hi = h->first ? 0 : S.xhint_hi;
     p.wrap_z = h->wrap_z;
     p.tau = h->tau;
     p.omega = 1.0 / h->tau;
@@ -460,6 +478,12 @@ void fill_sweep_params(lbm_b200* h, SweepParams& p, int z0, bool with_peers, int
     for (int q = 0; q < h->Q; ++q) {
         p.srcq[q] = p.src + (long long) q * g.qstride - h->pull_offset[q];
         p.dstq[q] = p.dst + (long long) q * g.qstride;
+        // x-face guesses (kernels.cuh, sweep_kernel): bounce-back -> the cell's own inverse population,
+        // periodic -> the same pull one period further along x
+        const int cx = h->cvel_x[q];
+        const int hint = cx > 0 ? p.xhint_lo : (cx < 0 ? p.xhint_hi : 0);
+        p.altq[q] = hint == 1 ? p.src + (long long) (h->Q - 1 - q) * g.qstride
+                  : hint == 2 ? p.srcq[q] + cx * g.xl : p.srcq[q];
     }
     const int bx = 1 << shift, by = LBM_SWEEP_THREADS >> shift;
     grid_xy[0] = (g.xl + bx - 1) / bx;
@@ -477,7 +501,10 @@ int launch_sweep(lbm_b200* h, int z0, int nz, bool with_peers, int z_step, int m
         constexpr int Q = decltype(Qc)::value;
         auto go = [&](auto Ex) {
             constexpr bool EX = decltype(Ex)::value;
-            if (mode == SWEEP_SPLIT) sweep_kernel<Q, EX, SWEEP_SPLIT><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+            // x-face guesses only where the host has one for this source layer (and never on the first step)
+            const bool xface = mode == SWEEP_SPECULATIVE && h->xface_mode != 0 && (p.xhint_lo | p.xhint_hi) != 0;
+            if (xface) sweep_kernel<Q, EX, SWEEP_XFACE><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
+            else if (mode == SWEEP_SPLIT) sweep_kernel<Q, EX, SWEEP_SPLIT><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
             else if (mode == SWEEP_CHECKED) sweep_kernel<Q, EX, SWEEP_CHECKED><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
             else sweep_kernel<Q, EX, SWEEP_SPECULATIVE><<<grid, LBM_SWEEP_THREADS, 0, h->stream>>>(p);
         };
@@ -592,6 +619,8 @@ int preload_step_kernels(int Q)
         cudaFuncGetAttributes(&a, sweep_kernel<QQ, false, SWEEP_SPECULATIVE>);
         cudaFuncGetAttributes(&a, sweep_kernel<QQ, false, SWEEP_CHECKED>);
         cudaFuncGetAttributes(&a, sweep_kernel<QQ, false, SWEEP_SPLIT>);
+        cudaFuncGetAttributes(&a, sweep_kernel<QQ, false, SWEEP_XFACE>);
+        cudaFuncGetAttributes(&a, sweep_kernel<QQ, true, SWEEP_XFACE>);
         cudaFuncGetAttributes(&a, sweep_kernel<QQ, true, SWEEP_SPECULATIVE>);
         cudaFuncGetAttributes(&a, sweep_kernel<QQ, true, SWEEP_CHECKED>);
         cudaFuncGetAttributes(&a, sweep_kernel<QQ, true, SWEEP_SPLIT>);
@@ -930,12 +959,16 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl_all, uint64_
     h->tau = tau;
     if (const char* e = getenv("LBM_B200_GRAPHS")) h->graph_mode = atoi(e);
     if (const char* e = getenv("LBM_B200_SWEEP_MODE")) h->sweep_mode = std::max(-1, std::min(1, atoi(e)));
+    if (const char* e = getenv("LBM_B200_XFACE")) h->xface_mode = atoi(e) != 0;
     if (const char* e = getenv("LBM_B200_TMA")) h->tma_mode = std::max(-1, std::min(1, atoi(e)));
     {
         double vel[27 * 3];
         lbm_b200_model(Q, vel, nullptr);
         for (int q = 0; q < Q; ++q)
+        {
             h->pull_offset[q] = (long long) vel[3 * q + 2] * h->g.sz + (long long) vel[3 * q + 1] * h->g.sy + (long long) vel[3 * q];
+            h->cvel_x[q] = (int) vel[3 * q];
+        }
     }
     *out = h;   // so that the caller can destroy on failure below
     DeviceGuard guard(device);
@@ -1785,6 +1818,22 @@ bool device_cpus(int device, cpu_set_t* set)
     }
     return count > 0;
 }
+}
+
+int lbm_b200_selftest_division(uint64_t n, uint64_t seed, double tau, uint64_t* mismatches)
+{
+    if (!mismatches || !(tau > 0.0)) return fail(LBM_B200_EINVAL, "bad self-test request");
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, sizeof *d) != cudaSuccess) return fail(LBM_B200_ECUDA, "no CUDA device for the division self-test");
+    cudaMemset(d, 0, sizeof *d);
+    for (int which = 0; which < 5; ++which)
+        division_selftest_kernel<<<148 * 8, 256>>>(n, seed + which, which, tau, 1.0 / tau, d);
+    unsigned long long bad = 0;
+    const cudaError_t e = cudaMemcpy(&bad, d, sizeof bad, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LBM_B200_ECUDA, "division self-test failed: %s", cudaGetErrorString(e));
+    *mismatches = bad;
+    return 0;
 }
 
 int lbm_b200_bind_host_thread(int device)

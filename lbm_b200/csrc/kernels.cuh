@@ -78,6 +78,9 @@ struct SweepParams {
     int z_step;        // plane stride between consecutive blockIdx.z (1, or zl-1 for the two edge planes)
     int bx_shift;      // log2(threads along x per block)
     int first;         // 1: boundary cells still hold host-visible values -> pull stored
+    int xhint_lo, xhint_hi;   // what most cells of the x = 1 / x = xl face see in the ghost plane next to them (0: unknown,
+                       // 1: NoSlipBoundary, 2: PERIODIC): their pulls out of that plane are pointed at the values
+                       // the wall path would fetch, and kept if the link mask then confirms the guess
     int wrap_z;        // the periodic slow axis is closed inside this slab
     double tau;
     double omega;      // 1/tau (fast mode)
@@ -86,6 +89,7 @@ struct SweepParams {
     //   srcq[q] = src + q*qstride - (cz*plane + cy*P + cx),   dstq[q] = dst + q*qstride
     const double* srcq[27];
     double* dstq[27];
+    const double* altq[27];   // c_x != 0: where an x-face cell pulls instead when the face's hint is set (see sweep_kernel)
     // optional remote copies of the slab-edge populations (peer ghost planes)
     double* up_dst;    // receives the c_slow=+1 populations of the last plane of the slow axis
     double* dn_dst;    // receives the c_slow=-1 populations of its first plane
@@ -134,6 +138,70 @@ template <> struct Ar<true> {
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
 };
 
+// Correctly rounded quotient a / b from y = RN(1 / b), without a division: the reference divides by the same
+// few values all the time (C_S*C_S, 2*C_S^4, 2*C_S^2, tau: constants; rho: three times per cell), 61 / 85
+// IEEE divisions per D3Q19 / D3Q27 cell, which made the bit-identical mode 3x slower than the fast one.
+//   q0 = RN(a*y)          |q0 - a/b| < 1.5 ulp   (y carries a relative error < 2^-53)
+//   q1 = RN(q0 + r0*y),   r0 = RN(a - b*q0)      -> q1 is a FAITHFUL rounding of a/b (error of r0*y << 1 ulp)
+//   q2 = RN(q1 + r1*y),   r1 = a - b*q1 (exact)  -> q2 = RN(a/b): Markstein's theorem (IBM J. R&D 34, 1990: q faithful,
+//                                                  y within 2^-53 relative of 1/b, residual by FMA => correct rounding)
+// Valid while the residuals neither underflow nor overflow (|a| and |a/b| within 2^+-900) and a is not -0:
+// every dividend on this path is +0 or a sum / product of O(1e-18 .. 1) numbers.  Non-finite states (a run
+// that has blown up) may propagate NaN where the reference still holds inf.  tools/selftest/div_check.c and
+// lbm_b200_selftest_division compare the sequence with IEEE division on 10^8 operands.
+#ifndef LBM_EXACT_DIV          // 0: IEEE divisions (__ddiv_rn) as in round 1, 1: the sequence above
+#define LBM_EXACT_DIV 1
+#endif
+#ifndef LBM_DIV_STEPS          // 2 = proven; 1 = one correction only (measurement knob, NOT proven for q0 off by > 1 ulp)
+#define LBM_DIV_STEPS 2
+#endif
+__device__ __forceinline__ double div_rcp(double a, double b, double y)
+{
+#if LBM_EXACT_DIV
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+#if LBM_DIV_STEPS >= 2
+    r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+#endif
+    return q;
+#else
+    return __ddiv_rn(a, b);
+#endif
+}
+constexpr double RCP_CS2 = 1.0 / CS2, RCP_TWO_CS4 = 1.0 / TWO_CS4, RCP_TWO_CS2 = 1.0 / TWO_CS2;   // correctly rounded
+__device__ __forceinline__ double div_cs2(double a) { return div_rcp(a, CS2, RCP_CS2); }
+__device__ __forceinline__ double div_two_cs4(double a) { return div_rcp(a, TWO_CS4, RCP_TWO_CS4); }
+__device__ __forceinline__ double div_two_cs2(double a) { return div_rcp(a, TWO_CS2, RCP_TWO_CS2); }
+// 1 / b for a run-time divisor used several times (rho): one correctly rounded reciprocal
+__device__ __forceinline__ double rcp_exact(double b)
+{
+#if LBM_EXACT_DIV
+    return __drcp_rn(b);
+#else
+    return 0.0;
+#endif
+}
+
+// c_dot_u of collision.hpp:40-44, ((0 + c0*u0) + c1*u1) + c2*u2.  Terms with c = 0 are skipped and c = +-1 is
+// an add / subtract: +-1 * u is exact, 0 * u = +-0 leaves a sum that is never -0 untouched (the chain starts
+// from +0, and x + (-x) = +0), so the bits are the reference's for all finite u.
+template <int Q, int q>
+__device__ __forceinline__ double cu_exact(double ux, double uy, double uz)
+{
+    using L = Lattice<Q>;
+    using A = Ar<true>;
+    double cu = 0.0;
+    if constexpr (L::cx(q) == 1) cu = A::add(cu, ux);
+    if constexpr (L::cx(q) == -1) cu = A::sub(cu, ux);
+    if constexpr (L::cy(q) == 1) cu = A::add(cu, uy);
+    if constexpr (L::cy(q) == -1) cu = A::sub(cu, uy);
+    if constexpr (L::cz(q) == 1) cu = A::add(cu, uz);
+    if constexpr (L::cz(q) == -1) cu = A::sub(cu, uz);
+    return cu;
+}
+
 // collision.hpp:34-51, one entry; uu_term = u_dot_u / (2*C_S*C_S) is the same
 // value for every q in the reference and is hoisted by the callers.
 template <int Q, int q>
@@ -141,14 +209,27 @@ __device__ __forceinline__ double feq_exact(double rho, double ux, double uy, do
 {
     using L = Lattice<Q>;
     using A = Ar<true>;
-    constexpr double cx = L::cx(q), cy = L::cy(q), cz = L::cz(q);
-    double cu = A::add(0.0, A::mul(cx, ux));
-    cu = A::add(cu, A::mul(cy, uy));
-    cu = A::add(cu, A::mul(cz, uz));
-    double t = A::add(1.0, A::div(cu, CS2));
-    t = A::add(t, A::div(A::mul(cu, cu), TWO_CS4));
+    const double cu = cu_exact<Q, q>(ux, uy, uz);
+    double t = A::add(1.0, div_cs2(cu));
+    t = A::add(t, div_two_cs4(A::mul(cu, cu)));
     t = A::sub(t, uu_term);
     return A::mul(A::mul(L::w(q), rho), t);
+}
+// feq of direction q and of its inverse at once: c_dot_u of the inverse is -c_dot_u bit for bit (or both +0),
+// a quotient changes sign with its dividend, 1 + (-d) = 1 - d, and the square is shared.
+template <int Q, int q>
+__device__ __forceinline__ void feq_pair_exact(double rho, double ux, double uy, double uz, double uu_term,
+                                               double& e, double& e_inv)
+{
+    using L = Lattice<Q>;
+    using A = Ar<true>;
+    static_assert(L::w(q) == L::w(L::inv(q)), "opposite directions share their weight");
+    const double cu = cu_exact<Q, q>(ux, uy, uz);
+    const double d1 = div_cs2(cu);
+    const double d2 = div_two_cs4(A::mul(cu, cu));
+    const double wr = A::mul(L::w(q), rho);
+    e = A::mul(wr, A::sub(A::add(A::add(1.0, d1), d2), uu_term));
+    e_inv = A::mul(wr, A::sub(A::add(A::sub(1.0, d1), d2), uu_term));
 }
 __device__ __forceinline__ double uu_term_exact(double ux, double uy, double uz)
 {
@@ -156,23 +237,43 @@ __device__ __forceinline__ double uu_term_exact(double ux, double uy, double uz)
     double uu = A::add(0.0, A::mul(ux, ux));
     uu = A::add(uu, A::mul(uy, uy));
     uu = A::add(uu, A::mul(uz, uz));
-    return A::div(uu, TWO_CS2);
+    return div_two_cs2(uu);
+}
+
+// one term of compute_density / compute_velocity (collision.hpp:7-31): rho += v; m += v * c.  c = 0 terms add
+// +-0 to sums that are never -0 and are skipped, c = +-1 is an add / subtract -- same bits for finite v.
+template <int Q, int q>
+__device__ __forceinline__ void moment_term_exact(double v, double& rho, double& mx, double& my, double& mz)
+{
+    using L = Lattice<Q>;
+    using A = Ar<true>;
+    rho = A::add(rho, v);
+    if constexpr (L::cx(q) == 1) mx = A::add(mx, v);
+    if constexpr (L::cx(q) == -1) mx = A::sub(mx, v);
+    if constexpr (L::cy(q) == 1) my = A::add(my, v);
+    if constexpr (L::cy(q) == -1) my = A::sub(my, v);
+    if constexpr (L::cz(q) == 1) mz = A::add(mz, v);
+    if constexpr (L::cz(q) == -1) mz = A::sub(mz, v);
 }
 
 // moments of a register-resident cell: collision.hpp:7-31
 template <int Q>
 __device__ __forceinline__ void moments_exact(const double (&f)[Q], double& rho, double& mx, double& my, double& mz)
 {
-    using L = Lattice<Q>;
-    using A = Ar<true>;
     rho = 0.0; mx = 0.0; my = 0.0; mz = 0.0;
     static_for<Q>([&](auto I) {
         constexpr int q = decltype(I)::value;
-        rho = A::add(rho, f[q]);
-        mx = A::add(mx, A::mul(f[q], (double) L::cx(q)));
-        my = A::add(my, A::mul(f[q], (double) L::cy(q)));
-        mz = A::add(mz, A::mul(f[q], (double) L::cz(q)));
+        moment_term_exact<Q, q>(f[q], rho, mx, my, mz);
     });
+}
+
+// u = m / rho (collision.hpp:27-29): three quotients by the same divisor
+__device__ __forceinline__ void velocity_exact(double rho, double mx, double my, double mz, double& ux, double& uy, double& uz)
+{
+    const double ir = rcp_exact(rho);
+    ux = div_rcp(mx, rho, ir);
+    uy = div_rcp(my, rho, ir);
+    uz = div_rcp(mz, rho, ir);
 }
 
 template <int Q, bool EXACT>
@@ -181,14 +282,23 @@ __device__ __forceinline__ void bgk_collide(double (&f)[Q], double tau, double o
     using L = Lattice<Q>;
     if constexpr (EXACT) {
         using A = Ar<true>;
-        double rho, mx, my, mz;
+        double rho, mx, my, mz, ux, uy, uz;
         moments_exact<Q>(f, rho, mx, my, mz);
-        const double ux = A::div(mx, rho), uy = A::div(my, rho), uz = A::div(mz, rho);
+        velocity_exact(rho, mx, my, mz, ux, uy, uz);
         const double uut = uu_term_exact(ux, uy, uz);
-        static_for<Q>([&](auto I) {
+        // f -= (f - feq) / tau, collision.hpp:68; omega = RN(1 / tau) from the host
+        static_for<(Q + 1) / 2>([&](auto I) {
             constexpr int q = decltype(I)::value;
-            const double e = feq_exact<Q, q>(rho, ux, uy, uz, uut);
-            f[q] = A::sub(f[q], A::div(A::sub(f[q], e), tau));      // collision.hpp:68
+            constexpr int qi = L::inv(q);
+            if constexpr (q == qi) {
+                const double e = feq_exact<Q, q>(rho, ux, uy, uz, uut);
+                f[q] = A::sub(f[q], div_rcp(A::sub(f[q], e), tau, omega));
+            } else {
+                double e, ei;
+                feq_pair_exact<Q, q>(rho, ux, uy, uz, uut, e, ei);
+                f[q] = A::sub(f[q], div_rcp(A::sub(f[q], e), tau, omega));
+                f[qi] = A::sub(f[qi], div_rcp(A::sub(f[qi], ei), tau, omega));
+            }
         });
     } else {
         // same formula, reciprocals and free contraction; opposite directions
@@ -233,22 +343,34 @@ __device__ __forceinline__ void bgk_collide(double (&f)[Q], double tau, double o
 struct OwnMoments {
     double rho, mx, my, mz;
     bool have;
+    // OutflowBoundary / PressureBoundary: velocity = momentum / REFERENCE density of handler `rec_of_u`
+    // (boundary.hpp:144, 209) and its u.u term, the same for every link of one handler
+    double ux, uy, uz, uut;
+    const void* rec_of_u;
 };
 
-// sequential moments of the cell at index i of `src` (collision.hpp:7-31)
+// sequential moments of the cell at index i of `src` (collision.hpp:7-31); the sums keep the reference's order.
+// Out of line on purpose: at the call sites the Q pulled values are live, and the callee gets by with few registers
+// (ptxas then loads and adds one population after the other whatever the batch size -- measured: batches of 1, 9 and
+// Q within 1 % of each other on the channel config, profiles/variants_r09_exact_wall.txt).
+#ifndef LBM_MOM_BATCH
+#define LBM_MOM_BATCH 9
+#endif
 template <int Q>
 __device__ __noinline__ void load_moments(const double* __restrict__ src, long long qstride, int i, OwnMoments* m)
 {
-    const Tables<Q>& T = tables<Q>();
+    constexpr int B = LBM_MOM_BATCH < 1 ? Q : LBM_MOM_BATCH;
     double rho = 0.0, mx = 0.0, my = 0.0, mz = 0.0;
-    #pragma unroll 1
-    for (int q = 0; q < Q; ++q) {
-        const double v = src[q * qstride + i];
-        rho = __dadd_rn(rho, v);
-        mx = __dadd_rn(mx, __dmul_rn(v, (double) T.c[q][0]));
-        my = __dadd_rn(my, __dmul_rn(v, (double) T.c[q][1]));
-        mz = __dadd_rn(mz, __dmul_rn(v, (double) T.c[q][2]));
-    }
+    static_for<(Q + B - 1) / B>([&](auto C) {
+        constexpr int q0 = decltype(C)::value * B;
+        constexpr int n = Q - q0 < B ? Q - q0 : B;
+        double v[n];
+        static_for<n>([&](auto J) { constexpr int j = decltype(J)::value; v[j] = src[(q0 + j) * qstride + i]; });
+        static_for<n>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            moment_term_exact<Q, q0 + j>(v[j], rho, mx, my, mz);
+        });
+    });
     m->rho = rho; m->mx = mx; m->my = my; m->mz = mz; m->have = true;
 }
 
@@ -298,7 +420,7 @@ __device__ __forceinline__ double link_value(const double* __restrict__ src, con
         cu = __dadd_rn(cu, __dmul_rn(cz, rec->v[2]));
         constexpr double two_w = 2.0 * L::w(q);
         if constexpr (EXACT) {
-            return __dadd_rn(finv, __ddiv_rn(__dmul_rn(__dmul_rn(two_w, om.rho), cu), CS2));
+            return __dadd_rn(finv, div_cs2(__dmul_rn(__dmul_rn(two_w, om.rho), cu)));
         } else {
             return finv + two_w * om.rho * cu * (1.0 / CS2);
         }
@@ -309,10 +431,15 @@ __device__ __forceinline__ double link_value(const double* __restrict__ src, con
     case K_PRESSURE: {                                        // boundary.hpp:208-211
         if (!om.have) load_moments<Q>(src, g.qstride, iX, &om);
         const double r = rec->rho;                            // momentum / REFERENCE density
-        const double ux = __ddiv_rn(om.mx, r), uy = __ddiv_rn(om.my, r), uz = __ddiv_rn(om.mz, r);
-        const double uut = uu_term_exact(ux, uy, uz);
-        const double e = feq_exact<Q, q>(r, ux, uy, uz, uut);
-        const double ei = feq_exact<Q, qi>(r, ux, uy, uz, uut);
+        if (om.rec_of_u != (const void*) rec) {               // once per handler, not once per link
+            velocity_exact(r, om.mx, om.my, om.mz, om.ux, om.uy, om.uz);
+            om.uut = uu_term_exact(om.ux, om.uy, om.uz);
+            om.rec_of_u = rec;
+        }
+        double e, ei;
+        if constexpr (q < qi) feq_pair_exact<Q, q>(r, om.ux, om.uy, om.uz, om.uut, e, ei);
+        else if constexpr (q > qi) feq_pair_exact<Q, qi>(r, om.ux, om.uy, om.uz, om.uut, ei, e);
+        else e = ei = feq_exact<Q, q>(r, om.ux, om.uy, om.uz, om.uut);
         return __dsub_rn(__dadd_rn(e, ei), src[qi * g.qstride + iX]);
     }
     case K_FREESLIP:
@@ -395,6 +522,7 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
         const BcRec* rec = p.bc + p.bcid[s0];
         OwnMoments om;
         om.have = false;
+        om.rec_of_u = nullptr;
         static_for<Q>([&](auto I) {
             constexpr int q = decltype(I)::value;
             if (m & (1u << q)) f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, rec, om);
@@ -402,6 +530,7 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
     } else if (m != 0) {
         OwnMoments om;
         om.have = false;
+        om.rec_of_u = nullptr;
         static_for<Q>([&](auto I) {
             constexpr int q = decltype(I)::value;
             if (m & (1u << q)) {
@@ -464,11 +593,29 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
 //   SWEEP_CHECKED      looks at the bit (L2-resident map) BEFORE pulling: a solid cell costs one map read instead
 //                      of Q wasted pulls -- for geometries with large solid regions (pipe.vtk: 44 % solid).
 //   SWEEP_SPLIT        SWEEP_CHECKED for lattices that carry different handlers (MASK_NOCOLLIDE cells exist)
-enum : int { SWEEP_SPECULATIVE = 0, SWEEP_CHECKED = 1, SWEEP_SPLIT = 2 };
+//   SWEEP_XFACE        SWEEP_SPECULATIVE + guessed pulls for the cells of the two x faces (see sweep_kernel); chosen by the
+//                      host when it has a guess (SweepParams::xhint_*).  Its own instantiation: the address selection
+//                      costs a config without a guess 4-6 % (channel: inflow / outflow faces, profiles/variants_r10_xface.txt)
+enum : int { SWEEP_SPECULATIVE = 0, SWEEP_CHECKED = 1, SWEEP_SPLIT = 2, SWEEP_XFACE = 3 };
+
+// bits of the directions with c_x = sign (the pulls of an x-face cell that leave the interior)
+template <int Q>
+constexpr uint32_t x_leaving_mask(int sign)
+{
+    uint32_t m = 0;
+    for (int q = 0; q < Q; ++q)
+        if (Lattice<Q>::cx(q) == sign) m |= 1u << q;
+    return m;
+}
+#ifndef LBM_EAGER_MASK         // 1: cells of the six faces request their link mask together with the pulls
+#define LBM_EAGER_MASK 1
+#endif
 
 template <int Q, bool EXACT, int MODE>
 __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_kernel(const SweepParams p)
 {
+    using L = Lattice<Q>;
+    constexpr bool SPECULATIVE = MODE == SWEEP_SPECULATIVE || MODE == SWEEP_XFACE;
     const Layout& g = p.g;
     const int bx = 1 << p.bx_shift;
     const int x = 1 + blockIdx.x * bx + (threadIdx.x & (bx - 1));
@@ -480,20 +627,90 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
     // Bulk cells read 1/8 byte of map, not 4.
     const uint32_t word = p.bits[i >> 5];
     uint32_t m = 0;
-    if constexpr (MODE != SWEEP_SPECULATIVE) {
+    if constexpr (!SPECULATIVE) {
         if ((word >> (i & 31)) & 1u) {
             m = p.mask[i];
             if (m & MASK_SKIP) return;
         }
     }
+    // SPECULATIVE.  A cell of one of the six faces is almost always a wall cell: its link mask is requested now,
+    // together with the pulls, instead of after the bit map has arrived (one memory round trip less).
+    // XFACE.  Every row has two x-face cells, i.e. a quarter (512 cells per row) or half (256) of all warps carry one
+    // lane that walks the wall path -- mask, then the wall values, then collide -- while 31 lanes wait.  The host knows
+    // what most of those cells see next to them (xhint); for a NoSlipBoundary the wall value of direction q is the
+    // cell's own population inv(q) of the previous step (boundary.hpp:28), for a PERIODIC ghost plane it is the pull
+    // from the opposite face: the lane simply pulls THAT address instead of the ghost cell's.  If the mask then says
+    // exactly this (all flagged links are of the guessed kind and are the c_x = +-1 ones) the cell is done and joins
+    // the bulk lanes; otherwise the guessed directions are pulled again from their true sources and the wall path runs.
+    uint32_t m_eager = 0;
+    bool face = false;
+    int xs = 0, hint = 0;
+    if constexpr (SPECULATIVE) {
+        const bool yz_face = mid == 1 || mid == n_mid(g) || slow == 1 || slow == n_slow(g);
+#if LBM_EAGER_MASK
+        face = yz_face || x == 1 || x == g.xl;
+        if (face) m_eager = p.mask[i];
+#endif
+        if constexpr (MODE == SWEEP_XFACE) {
+            if (!yz_face) {        // (sources of an edge cell may wrap in y / z as well: left to the wall path)
+                if (x == 1) { xs = 1; hint = p.xhint_lo; }
+                else if (x == g.xl) { xs = -1; hint = p.xhint_hi; }
+            }
+        }
+    }
     double f[Q];
-    static_for<Q>([&](auto I) {
-        constexpr int q = decltype(I)::value;
-        f[q] = LBM_LD(p.srcq[q] + i);
-    });
-    if constexpr (MODE == SWEEP_SPECULATIVE) {
-        m = ((word >> (i & 31)) & 1u) ? p.mask[i] : 0u;
+    // Only the two warps of a row that hold an x-face lane select addresses (a warp-uniform branch): the selection
+    // (a per-lane choice between two constant-bank pointers for every c_x != 0 pull; altq = own inverse population
+    // for a bounce-back face, the pull one period further for a periodic one -- set up by the host) costs the loads
+    // of D3Q27 4-6 % when every warp carries it.
+    bool select = false;
+    if constexpr (MODE == SWEEP_XFACE) select = __any_sync(__activemask(), hint != 0);
+    if (select) {
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            const double* base = p.srcq[q];
+            if constexpr (L::cx(q) != 0) {
+                if (hint != 0 && xs == L::cx(q)) base = p.altq[q];
+            }
+            f[q] = LBM_LD(base + i);
+        });
+    } else {
+        static_for<Q>([&](auto I) {
+            constexpr int q = decltype(I)::value;
+            f[q] = LBM_LD(p.srcq[q] + i);
+        });
+    }
+    if constexpr (SPECULATIVE) {
+        // The pulls must be REQUESTED before anything waits for the maps.  ptxas otherwise moves the "not streamed"
+        // exit (which only needs the eagerly requested mask) in front of the pulls -- two dependent memory round
+        // trips per cell instead of one.  An exit cannot move across a warp barrier.
+        __syncwarp();
+#if defined(LBM_HACK_NOWALL) && LBM_HACK_NOWALL == 2     /* timing experiment only (wrong results): no wall path at all */
+        m = 0u;
+#elif defined(LBM_HACK_NOWALL)                           /* ... no wall path for the cells of the two x faces */
+        m = (((word >> (i & 31)) & 1u) && x != 1 && x != g.xl) ? p.mask[i] : 0u;
         if (m & MASK_SKIP) return;
+#else
+        m = ((word >> (i & 31)) & 1u) ? (face ? m_eager : p.mask[i]) : 0u;
+        if (m & MASK_SKIP) return;
+#endif
+        if constexpr (MODE == SWEEP_XFACE) {
+            if (hint != 0) {
+                constexpr uint32_t QBITS = (1u << Q) - 1u;
+                const uint32_t leaving = xs > 0 ? x_leaving_mask<Q>(1) : x_leaving_mask<Q>(-1);
+                const uint32_t all_of_kind = hint == 1 ? MASK_ALLNOSLIP : MASK_ALLPERIODIC;
+                if ((m & all_of_kind) && (m & QBITS) == leaving) {
+                    m = 0;                                   // guessed right: f[] already holds the wall values
+                } else {                                     // guessed wrong: pull the true sources, then the wall path as usual
+                    static_for<Q>([&](auto I) {
+                        constexpr int q = decltype(I)::value;
+                        if constexpr (L::cx(q) != 0) {
+                            if (xs == L::cx(q)) f[q] = LBM_LD(p.srcq[q] + i);
+                        }
+                    });
+                }
+            }
+        }
     }
     finish_cell<Q, EXACT, MODE == SWEEP_SPLIT>(p, f, m, i, x, y, z);
 }
@@ -766,6 +983,8 @@ __global__ void materialize_kernel(double* __restrict__ field, const uint8_t* __
             if (kind[n] == K_FLUID) {
                 OwnMoments om;
                 om.have = false;
+                om.rec_of_u = nullptr;
+        om.rec_of_u = nullptr;
                 field[q * g.qstride + b] = link_value<Q, EXACT, q>(field, kind, g, n, k, rec, om);
             }
         }
@@ -901,6 +1120,18 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ kind_src, const ui
     }
     mask[i] = m;
     if (m) atomicOr(&bits[i >> 5], 1u << (i & 31));   // bits zeroed by the caller
+    // x-face statistics for SweepParams::xhint_*: cells (not on a y / z face) of the x = 1 / x = xl face whose flagged
+    // links are exactly the c_x = +1 / -1 ones and all NoSlipBoundary (counters[8], [10]) or all PERIODIC ([9], [11])
+    if (streamed && (x == 1 || x == g.xl) && y > 1 && y < g.yl && z > 1 && z < g.zl) {
+        const int sign = x == 1 ? 1 : -1;
+        uint32_t leaving = 0;
+        for (int q = 0; q < Q; ++q)
+            if (T.c[q][0] == sign) leaving |= 1u << q;
+        if ((m & ((1u << Q) - 1u)) == leaving) {
+            if (m & MASK_ALLNOSLIP) atomicAdd(&counters[x == 1 ? 8 : 10], 1u);
+            if (m & MASK_ALLPERIODIC) atomicAdd(&counters[x == 1 ? 9 : 11], 1u);
+        }
+    }
     if ((m & MASK_SKIP) && interior) atomicAdd(&counters[3], 1u);
     const int slow = g.swap ? y : z;
     const bool neighbours_cell = (slow == 0 && lo_interface) || (slow == n_slow(g) + 1 && hi_interface);
@@ -1083,6 +1314,42 @@ __global__ void equilibrium_kernel(const double* __restrict__ rho, const double*
         constexpr int q = decltype(I)::value;
         field[q * g.qstride + i] = feq_exact<Q, q>(r, ux, uy, uz, uut);
     });
+}
+
+// Self-test of div_rcp against IEEE division (lbm_b200_selftest_division): operand n of divisor set `which`
+// (0: C_S^2, 1: 2 C_S^4, 2: 2 C_S^2, 3: tau, 4: a random rho-like divisor per operand) is a hash of (seed, n) with a
+// random 52-bit mantissa and an exponent in 2^-60 .. 2^4 -- the magnitudes the sweep divides.
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void division_selftest_kernel(unsigned long long n, unsigned long long seed, int which, double tau, double rcp_tau,
+                                         unsigned long long* __restrict__ mismatches)
+{
+    unsigned long long bad = 0;
+    for (unsigned long long k = blockIdx.x * (unsigned long long) blockDim.x + threadIdx.x; k < n;
+         k += (unsigned long long) gridDim.x * blockDim.x) {
+        const uint64_t h = mix64(seed * 0x100000001B3ull + k), h2 = mix64(h);
+        const uint64_t e = 1023 - 60 + (h2 >> 8) % 65;
+        const double a = __longlong_as_double((long long) (((h2 & 1) << 63) | (e << 52) | (h >> 12)));
+        double b, y;
+        switch (which) {
+        case 0: b = CS2; y = RCP_CS2; break;
+        case 1: b = TWO_CS4; y = RCP_TWO_CS4; break;
+        case 2: b = TWO_CS2; y = RCP_TWO_CS2; break;
+        case 3: b = tau; y = rcp_tau; break;
+        default: {
+            const uint64_t h3 = mix64(h2);
+            b = __longlong_as_double((long long) (((uint64_t) (1023 - 2 + (h3 >> 60) % 4) << 52) | (h3 >> 12)));
+            y = __drcp_rn(b);
+        }
+        }
+        if (__double_as_longlong(div_rcp(a, b, y)) != __double_as_longlong(__ddiv_rn(a, b))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // ---------------------------------------------------------------------------

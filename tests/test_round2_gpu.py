@@ -388,3 +388,11 @@ def test_checkpoint_keeps_both_lattices_and_rejects_mismatches(tmp_path):
         e.set_boxes(case["boxes"][:-1])
         with pytest.raises(capi.LbmError, match="geometry"):
             e.load_checkpoint(ck)
+
+
+def test_reciprocal_division_is_ieee_division():
+    """kernels.cuh div_rcp (the bit-identical mode's quotients by C_S^2, 2 C_S^4, 2 C_S^2, tau and rho from a correctly
+    rounded reciprocal + two FMA corrections) == __ddiv_rn on 5 x 2*10^7 operands per call, several tau / seeds"""
+    from lbm_b200 import capi
+    for seed, tau in ((1, 0.6), (2, 0.51), (3, 1.0), (4, 1.9999), (5, 0.75)):
+        assert capi.selftest_division(20_000_000, seed, tau) == 0
