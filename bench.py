@@ -340,7 +340,8 @@ def main():
                 "kernel": "sweep_kernel<%d,%s>" % (Q, "exact" if args.exact else "fast"),
                 "algorithmic_bytes_per_launch": bytes_per_cell * local_cells}
 
-    # ---- the price of bit-exactness: the same workload in EXACT arithmetic (79 fp64 divisions per cell)
+    # ---- the price of bit-exactness: the same workload in EXACT arithmetic (the reference's association, no FMA
+    #      contraction, correctly rounded quotients from reciprocals -- DESIGN.md section 2)
     exact_mlups = None
     if not args.exact and not args.no_exact:
         dom.set_arithmetic(capi.EXACT)

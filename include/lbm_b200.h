@@ -76,8 +76,10 @@ typedef struct {
 enum {
     LBM_B200_FAST = 0,  /* reciprocals + FMA contraction; differs from the       */
                         /* reference by rounding only (gate: 1e-12 relative)     */
-    LBM_B200_EXACT = 1  /* the reference's expression association with true      */
-                        /* divisions and no FMA: bit-identical to the CPU build  */
+    LBM_B200_EXACT = 1  /* the reference's expression association, no FMA        */
+                        /* contraction, correctly rounded quotients (computed    */
+                        /* from reciprocals, see lbm_b200_selftest_division):    */
+                        /* bit-identical to the CPU build                        */
 };
 
 /* population layouts for upload/download */

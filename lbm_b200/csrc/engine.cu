@@ -176,7 +176,6 @@ struct lbm_b200 {
     CUtensorMap tmap[2][2];                         // [buffer][shifted]: 4-D views (x, y, z, q) of the two lattices,
                                                     // box bx x 256/bx, and (bx+2) x 256/bx for populations with c_x != 0
     long long pull_offset[27] = {};                 // c_z*plane + c_y*P + c_x per direction
-    int cvel_x[27] = {};                            // c_x per direction
     unsigned long long* d_trace = nullptr;         // LBM_B200_HALO_TRACE=<file prefix>: wait-kernel timestamps
     static constexpr int TRACE_EPOCHS = 8192;
 
@@ -478,12 +477,6 @@ void fill_sweep_params(lbm_b200* h, SweepParams& p, int z0, bool with_peers, int
     for (int q = 0; q < h->Q; ++q) {
         p.srcq[q] = p.src + (long long) q * g.qstride - h->pull_offset[q];
         p.dstq[q] = p.dst + (long long) q * g.qstride;
-        // x-face guesses (kernels.cuh, sweep_kernel): bounce-back -> the cell's own inverse population,
-        // periodic -> the same pull one period further along x
-        const int cx = h->cvel_x[q];
-        const int hint = cx > 0 ? p.xhint_lo : (cx < 0 ? p.xhint_hi : 0);
-        p.altq[q] = hint == 1 ? p.src + (long long) (h->Q - 1 - q) * g.qstride
-                  : hint == 2 ? p.srcq[q] + cx * g.xl : p.srcq[q];
     }
     const int bx = 1 << shift, by = LBM_SWEEP_THREADS >> shift;
     grid_xy[0] = (g.xl + bx - 1) / bx;
@@ -965,10 +958,7 @@ int create_common(lbm_b200_t** out, int Q, uint64_t xl, uint64_t yl_all, uint64_
         double vel[27 * 3];
         lbm_b200_model(Q, vel, nullptr);
         for (int q = 0; q < Q; ++q)
-        {
             h->pull_offset[q] = (long long) vel[3 * q + 2] * h->g.sz + (long long) vel[3 * q + 1] * h->g.sy + (long long) vel[3 * q];
-            h->cvel_x[q] = (int) vel[3 * q];
-        }
     }
     *out = h;   // so that the caller can destroy on failure below
     DeviceGuard guard(device);

@@ -89,7 +89,6 @@ struct SweepParams {
     //   srcq[q] = src + q*qstride - (cz*plane + cy*P + cx),   dstq[q] = dst + q*qstride
     const double* srcq[27];
     double* dstq[27];
-    const double* altq[27];   // c_x != 0: where an x-face cell pulls instead when the face's hint is set (see sweep_kernel)
     // optional remote copies of the slab-edge populations (peer ghost planes)
     double* up_dst;    // receives the c_slow=+1 populations of the last plane of the slow axis
     double* dn_dst;    // receives the c_slow=-1 populations of its first plane
@@ -659,20 +658,22 @@ __global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_
         }
     }
     double f[Q];
-    // Only the two warps of a row that hold an x-face lane select addresses (a warp-uniform branch): the selection
-    // (a per-lane choice between two constant-bank pointers for every c_x != 0 pull; altq = own inverse population
-    // for a bounce-back face, the pull one period further for a periodic one -- set up by the host) costs the loads
-    // of D3Q27 4-6 % when every warp carries it.
+    // Only the two warps of a row that hold an x-face lane select addresses (a warp-uniform branch; the selection
+    // costs the loads of D3Q27 4-6 % when every warp carries it).  The guessed source of a c_x != 0 pull: bounce-back
+    // -> the cell's own population inv(q), reached through the base pointer of inv(q) (which has its own pull offset
+    // folded in: srcq[inv q] + i - c_q.strides = src[inv q][i]); periodic -> the same pull one period further along x.
     bool select = false;
     if constexpr (MODE == SWEEP_XFACE) select = __any_sync(__activemask(), hint != 0);
     if (select) {
         static_for<Q>([&](auto I) {
             constexpr int q = decltype(I)::value;
-            const double* base = p.srcq[q];
-            if constexpr (L::cx(q) != 0) {
-                if (hint != 0 && xs == L::cx(q)) base = p.altq[q];
+            if constexpr (L::cx(q) == 0) {
+                f[q] = LBM_LD(p.srcq[q] + i);
+            } else {
+                const bool mine = xs == L::cx(q);
+                if (mine && hint == 1) f[q] = LBM_LD(p.srcq[L::inv(q)] + (i - (L::cz(q) * g.sz + L::cy(q) * g.sy + L::cx(q))));
+                else f[q] = LBM_LD(p.srcq[q] + ((mine && hint == 2) ? i + L::cx(q) * g.xl : i));
             }
-            f[q] = LBM_LD(base + i);
         });
     } else {
         static_for<Q>([&](auto I) {

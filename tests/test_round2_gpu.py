@@ -396,3 +396,55 @@ def test_reciprocal_division_is_ieee_division():
     from lbm_b200 import capi
     for seed, tau in ((1, 0.6), (2, 0.51), (3, 1.0), (4, 1.9999), (5, 0.75)):
         assert capi.selftest_division(20_000_000, seed, tau) == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# guessed pulls of x-face cells (kernels.cuh SWEEP_XFACE): right guesses, wrong guesses, no guess
+def _xface_case(Q, seed=5):
+    xl, yl, zl = 12, 14, 12     # 120 cells per x face away from the edges; the patches spoil about a quarter of them
+    rng = np.random.default_rng(seed)
+    boxes = O.cavity_boxes(xl, yl, zl) + O.face_boxes(xl, yl, zl, [
+        ((0, 0, 3, 4, 2, 3), O.MOVINGWALL, (0.0, 0.02, -0.01)),      # a patch of another handler on the x = 0 face
+        ((xl + 1, xl + 1, 2, 4, 4, 7), O.INFLOW, (-0.02, 0.0, 0.0)),  # ... and on the x = xl+1 face
+        ((1, 2, 7, 8, 3, 4), O.NOSLIP),                               # an obstacle that touches the x = 1 cells
+    ])
+    f0 = rng.random(((xl + 2) * (yl + 2) * (zl + 2), Q)) * 0.1 + 0.05
+    return dict(xl=xl, yl=yl, zl=zl, boxes=boxes, f_init=f0)
+
+
+@pytest.mark.parametrize("Q", [15, 19, 27])
+def test_xface_guesses_bitwise_with_mixed_faces(Q, monkeypatch):
+    """most x-face cells see a NoSlipBoundary (the guess), some see a moving wall / an inflow / an obstacle:
+    both the confirmed and the refuted guesses must give the reference's populations, with and without the mode"""
+    from test_parity_gpu import run_gpu
+    case = _xface_case(Q)
+    cpu = run_cpu(Q, case, 7)
+    for xface in ("1", "0"):
+        monkeypatch.setenv("LBM_B200_XFACE", xface)
+        gpu = run_gpu(Q, case, 7, exact=True)
+        assert_bitwise("x-face guesses (LBM_B200_XFACE=%s)" % xface, gpu["f"], cpu["f"])
+        assert_bitwise("density", gpu["rho"], cpu["rho"])
+
+
+@pytest.mark.parametrize("Q", [15, 19, 27])
+def test_xface_guesses_periodic_with_patches(Q, monkeypatch):
+    """x periodic (the guess) except for a wall patch on each x face, y / z walls: guessed == unguessed, bit for bit,
+    in both arithmetic modes"""
+    from lbm_b200 import capi
+    xl, yl, zl = 16, 12, 11
+    rng = np.random.default_rng(11)
+    boxes = O.face_boxes(xl, yl, zl, [("z0", O.NOSLIP), ("zmax", O.MOVINGWALL, (0.03, 0.0, 0.0)), ("y0", O.NOSLIP),
+                                      ("ymax", O.NOSLIP), ("x0", O.PERIODIC), ("xmax", O.PERIODIC),
+                                      ((0, 0, 3, 5, 3, 5), O.NOSLIP), ((xl + 1, xl + 1, 2, 3, 2, 6), O.NOSLIP)])
+    f0 = rng.random(((xl + 2) * (yl + 2) * (zl + 2), Q)) * 0.1 + 0.05
+    for exact in (True, False):
+        got = {}
+        for xface in ("1", "0"):
+            monkeypatch.setenv("LBM_B200_XFACE", xface)
+            with capi.Domain(Q, xl, yl, zl, TAU, exact=exact) as d:
+                d.set_boxes(boxes)
+                d.upload(f0)
+                d.step(9)
+                got[xface] = d.download()
+        inner = cases.interior_index(xl, yl, zl)
+        assert_bitwise("periodic x faces with patches, exact=%s" % exact, got["1"][inner], got["0"][inner])

@@ -16,7 +16,7 @@ path = os.path.join(ROOT, "profiles", "sweep_traffic.json")
 d = json.load(open(path)) if os.path.exists(path) else {}
 used = []
 for rep in sys.argv[1:]:
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     H, U, V = rows[0], rows[1], rows[2]
     name = V[H.index("Kernel Name")]
