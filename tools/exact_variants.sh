@@ -10,7 +10,7 @@ one() {  # name so Q extra-flag label
 }
 for so in variants/liblbm_b200_*.so; do
   name=$(basename $so .so); name=${name#liblbm_b200_}
-  for Q in 19 27; do
+  for Q in ${QS:-19 27}; do
     one $name $PWD/$so $Q "" fast
     one $name $PWD/$so $Q "--exact" exact
   done
