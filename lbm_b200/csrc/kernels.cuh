@@ -458,9 +458,16 @@ __device__ __forceinline__ int wrap1(int v, int l) { return v < 1 ? v + l : (v >
 #ifndef LBM_SWEEP_THREADS
 #define LBM_SWEEP_THREADS 64
 #endif
-// resident blocks per SM the register allocator must allow, per lattice
-// (profiles/variants_r0*.txt: 1024 resident threads/SM at 64 registers for D3Q15/19,
-//  768 at 80 registers for D3Q27 -- more registers lose occupancy, fewer spill)
+// Resident 64-thread blocks per SM the register allocator must allow = the register budget of a launch.
+// Until the end of round 2 the answer was "as many threads as possible" (16 / 16 / 12 blocks = 64 / 64 / 80 registers): the
+// link mask was a dependent load and wall lanes were slow, so resident warps bought bandwidth.  With one memory round
+// trip per cell for (nearly) every lane the pulls of 512-640 threads keep the DRAM busy, and what costs now are the one
+// or two pulled values ptxas spills at 64 / 80 registers (their reload sits in front of the collision).  Sweep over the
+// budget (cavity 512^3, fraction of the measured HBM rate; profiles/variants_r11_registers.txt):
+//   D3Q15 fast   64: .979   72: .982   80: .987   96: .994 (natural count, 10 blocks)        exact  64: .982  80: .990  96: .977
+//   D3Q19 fast   64: .958   72: .973   80: .976   88: .974   96: .982   116: .990 (8 blocks)  exact  64: .943  80: .981  96: .985  126: .968
+//   D3Q27 fast   80: .933   96: .961   128: .968 (8 blocks)                                    exact  80: .909  96: .965  128: .973
+// The bit-checked modes (CHECKED / SPLIT: pipes, literal masks) keep the round-1 budgets: their pulls DO wait for a map.
 #ifndef LBM_MB15
 #define LBM_MB15 16
 #endif
@@ -470,7 +477,29 @@ __device__ __forceinline__ int wrap1(int v, int l) { return v < 1 ? v + l : (v >
 #ifndef LBM_MB27
 #define LBM_MB27 12
 #endif
-template <int Q> struct MinBlocks { static constexpr int value = Q == 15 ? LBM_MB15 : (Q == 19 ? LBM_MB19 : LBM_MB27); };
+#ifndef LBM_MB15_FAST
+#define LBM_MB15_FAST 9
+#endif
+#ifndef LBM_MB15_EXACT
+#define LBM_MB15_EXACT 12
+#endif
+#ifndef LBM_MB19_FAST
+#define LBM_MB19_FAST 8
+#endif
+#ifndef LBM_MB19_EXACT
+#define LBM_MB19_EXACT 9
+#endif
+#ifndef LBM_MB27_FAST
+#define LBM_MB27_FAST 8
+#endif
+#ifndef LBM_MB27_EXACT
+#define LBM_MB27_EXACT 8
+#endif
+template <int Q, bool EXACT, bool SPECULATIVE> struct MinBlocks {
+    static constexpr int value = !SPECULATIVE ? (Q == 15 ? LBM_MB15 : (Q == 19 ? LBM_MB19 : LBM_MB27))
+                               : EXACT ? (Q == 15 ? LBM_MB15_EXACT : (Q == 19 ? LBM_MB19_EXACT : LBM_MB27_EXACT))
+                                       : (Q == 15 ? LBM_MB15_FAST : (Q == 19 ? LBM_MB19_FAST : LBM_MB27_FAST));
+};
 #ifdef LBM_LOAD_CS
 #define LBM_LD(ptr) __ldcs(ptr)
 #else
@@ -611,7 +640,7 @@ constexpr uint32_t x_leaving_mask(int sign)
 #endif
 
 template <int Q, bool EXACT, int MODE>
-__global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q>::value) sweep_kernel(const SweepParams p)
+__global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q, EXACT, MODE == SWEEP_SPECULATIVE || MODE == SWEEP_XFACE>::value) sweep_kernel(const SweepParams p)
 {
     using L = Lattice<Q>;
     constexpr bool SPECULATIVE = MODE == SWEEP_SPECULATIVE || MODE == SWEEP_XFACE;
