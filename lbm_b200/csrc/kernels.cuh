@@ -466,7 +466,7 @@ __device__ __forceinline__ int wrap1(int v, int l) { return v < 1 ? v + l : (v >
 // budget (cavity 512^3, fraction of the measured HBM rate; profiles/variants_r11_registers.txt):
 //   D3Q15 fast   64: .979   72: .982   80: .987   96: .994 (natural count, 10 blocks)        exact  64: .982  80: .990  96: .977
 //   D3Q19 fast   64: .958   72: .973   80: .976   88: .974   96: .982   116: .990 (8 blocks)  exact  64: .943  80: .981  96: .985  126: .968
-//   D3Q27 fast   80: .933   96: .961   128: .968 (8 blocks)                                    exact  80: .909  96: .965  128: .973
+//   D3Q27 fast   80: .933   96: .961   128: .968 (8 blocks)   148: .981 (6 blocks, x-face mode only)   exact  80: .909  96: .965  128: .973  160: .954
 // The bit-checked modes (CHECKED / SPLIT: pipes, literal masks) keep the round-1 budgets: their pulls DO wait for a map.
 #ifndef LBM_MB15
 #define LBM_MB15 16
@@ -495,10 +495,16 @@ __device__ __forceinline__ int wrap1(int v, int l) { return v < 1 ? v + l : (v >
 #ifndef LBM_MB27_EXACT
 #define LBM_MB27_EXACT 8
 #endif
-template <int Q, bool EXACT, bool SPECULATIVE> struct MinBlocks {
-    static constexpr int value = !SPECULATIVE ? (Q == 15 ? LBM_MB15 : (Q == 19 ? LBM_MB19 : LBM_MB27))
+// D3Q27, fast arithmetic, x-face guesses in use (every lane is a one-round-trip lane): 6 blocks = 148 registers reach 0.981;
+// the same budget without the guesses (channel: inflow / outflow lanes walk the wall path) loses 12 %, so only SWEEP_XFACE gets it
+#ifndef LBM_MB27_FAST_XFACE
+#define LBM_MB27_FAST_XFACE 6
+#endif
+template <int Q, bool EXACT, int MODE> struct MinBlocks {     // MODE: the SWEEP_* enum below (0 speculative, 3 x-face guesses)
+    static constexpr bool speculative = MODE == 0 || MODE == 3;
+    static constexpr int value = !speculative ? (Q == 15 ? LBM_MB15 : (Q == 19 ? LBM_MB19 : LBM_MB27))
                                : EXACT ? (Q == 15 ? LBM_MB15_EXACT : (Q == 19 ? LBM_MB19_EXACT : LBM_MB27_EXACT))
-                                       : (Q == 15 ? LBM_MB15_FAST : (Q == 19 ? LBM_MB19_FAST : LBM_MB27_FAST));
+                                       : (Q == 15 ? LBM_MB15_FAST : (Q == 19 ? LBM_MB19_FAST : (MODE == 3 ? LBM_MB27_FAST_XFACE : LBM_MB27_FAST)));
 };
 #ifdef LBM_LOAD_CS
 #define LBM_LD(ptr) __ldcs(ptr)
@@ -625,6 +631,7 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
 //                      host when it has a guess (SweepParams::xhint_*).  Its own instantiation: the address selection
 //                      costs a config without a guess 4-6 % (channel: inflow / outflow faces, profiles/variants_r10_xface.txt)
 enum : int { SWEEP_SPECULATIVE = 0, SWEEP_CHECKED = 1, SWEEP_SPLIT = 2, SWEEP_XFACE = 3 };
+static_assert(SWEEP_SPECULATIVE == 0 && SWEEP_XFACE == 3, "MinBlocks (above) names these two modes by value");
 
 // bits of the directions with c_x = sign (the pulls of an x-face cell that leave the interior)
 template <int Q>
@@ -640,7 +647,7 @@ constexpr uint32_t x_leaving_mask(int sign)
 #endif
 
 template <int Q, bool EXACT, int MODE>
-__global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q, EXACT, MODE == SWEEP_SPECULATIVE || MODE == SWEEP_XFACE>::value) sweep_kernel(const SweepParams p)
+__global__ void __launch_bounds__(LBM_SWEEP_THREADS, MinBlocks<Q, EXACT, MODE>::value) sweep_kernel(const SweepParams p)
 {
     using L = Lattice<Q>;
     constexpr bool SPECULATIVE = MODE == SWEEP_SPECULATIVE || MODE == SWEEP_XFACE;
