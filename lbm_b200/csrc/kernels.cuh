@@ -355,10 +355,12 @@ struct OwnMoments {
 #ifndef LBM_MOM_BATCH
 #define LBM_MOM_BATCH 9
 #endif
-template <int Q>
-__device__ __noinline__ void load_moments(const double* __restrict__ src, long long qstride, int i, OwnMoments* m)
+#ifndef LBM_MOM_INLINE         // 1: single-handler wall cells sum their own moments inline, all Q loads at once
+#define LBM_MOM_INLINE 1
+#endif
+template <int Q, int B>
+__device__ __forceinline__ void sum_moments(const double* __restrict__ src, long long qstride, int i, OwnMoments* m)
 {
-    constexpr int B = LBM_MOM_BATCH < 1 ? Q : LBM_MOM_BATCH;
     double rho = 0.0, mx = 0.0, my = 0.0, mz = 0.0;
     static_for<(Q + B - 1) / B>([&](auto C) {
         constexpr int q0 = decltype(C)::value * B;
@@ -371,6 +373,11 @@ __device__ __noinline__ void load_moments(const double* __restrict__ src, long l
         });
     });
     m->rho = rho; m->mx = mx; m->my = my; m->mz = mz; m->have = true;
+}
+template <int Q>
+__device__ __noinline__ void load_moments(const double* __restrict__ src, long long qstride, int i, OwnMoments* m)
+{
+    sum_moments<Q, (LBM_MOM_BATCH < 1 ? Q : LBM_MOM_BATCH)>(src, qstride, i, m);
 }
 
 // FreeSlipBoundary::collide, boundary.hpp:98-112, for the link (B, q), B = X - c_q.
@@ -557,6 +564,11 @@ __device__ __forceinline__ void finish_cell(const SweepParams& p, double (&f)[Q]
         OwnMoments om;
         om.have = false;
         om.rec_of_u = nullptr;
+#if LBM_MOM_INLINE
+        // with 96-148 registers the own populations of the cell fit next to the pulled ones: all Q loads of the moment sum
+        // in flight at once, inlined here (the out-of-line version loads and adds one after the other)
+        if (k == K_MOVINGWALL || k == K_OUTFLOW || k == K_PRESSURE) sum_moments<Q, Q>(p.src, g.qstride, i, &om);
+#endif
         static_for<Q>([&](auto I) {
             constexpr int q = decltype(I)::value;
             if (m & (1u << q)) f[q] = link_value<Q, EXACT, q>(p.src, p.kind, g, i, k, rec, om);
