@@ -304,6 +304,11 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    if world > 1:
+        # set-up, not warm-up: the first epochs of the peer hand-shake touch the freshly mapped IPC regions of both
+        # neighbours; let every rank get through them before the W warm-up steps the contract asks for
+        run.step(4)
+        barrier()
     run.step(args.warmup)
     barrier()
     launches0 = dom.launch_count()
